@@ -1,0 +1,126 @@
+"""The CPU oracle against the golden vectors produced by the REFERENCE's own code
+(oracle/make_golden.py).  Runs without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bls, dino_vit, feature_volume as fv, similarity as osim, synth
+
+
+def test_vit_param_counts():
+    # published DINO sizes (SURVEY.md §8c pin ii)
+    assert sum(p.numel() for p in dino_vit.build("vits8").parameters()) == 21_670_272
+    assert sum(p.numel() for p in dino_vit.build("vitb8").parameters()) == 85_807_872
+
+
+def test_dead_code_identity():
+    """Hooked K == LN1_L(x_{L-1}) W_k^T + b_k: the full forward with a hook and the
+    truncated evaluation agree bit-exactly."""
+    model = dino_vit.build("vits8", depth=3)
+    seen = []
+    h = model.blocks[-1].attn.qkv.register_forward_hook(lambda m, i, o: seen.append(o))
+    x = torch.randn(2, 3, 32, 48, generator=torch.Generator().manual_seed(1))
+    model(x)
+    h.remove()
+    assert torch.equal(seen[0].half(), fv.hooked_qkv(model, x))
+
+
+@pytest.mark.parametrize("name", ["feat_cube", "feat_noncubic"])
+def test_feature_volume_matches_reference(golden, name):
+    g = golden(name)
+    shape, fos, depth = tuple(int(v) for v in g["shape"]), int(g["fos"]), int(g["depth"])
+    vol, _ = synth.ct_volume(shape, n_shells=4, seed=int(g["seed_vol"]))
+    model = dino_vit.build("vits8", seed=int(g["seed_model"]), depth=depth)
+    k = fv.feature_volume(vol, model, patch=8, fos=fos, batch_size=2)
+    ref = torch.from_numpy(g["k"])
+    assert k.dtype == torch.float16 and k.shape == ref.shape
+    # batch size changes BLAS blocking -> last-bit fp32 differences before the fp16 rounding
+    assert (k.float() - ref.float()).abs().max() <= 2e-3
+    assert (k == ref).float().mean() > 0.99
+    im_sz, _ = fv.image_sizes(shape, 8, fos)
+    assert im_sz == tuple(int(v) for v in g["im_sz"])
+    ky = fv.k_features_axis(vol, model, 8, im_sz, "y", batch_size=2)
+    refy = torch.from_numpy(g["k_y_unpooled"])
+    assert ky.shape == refy.shape and (ky.float() - refy.float()).abs().max() <= 2e-3
+
+
+def _sim_inputs(g):
+    feats = torch.from_numpy(g["feats"])
+    names = [str(n) for n in g["ann_names"]]
+    pts = torch.from_numpy(g["ann_pts"])
+    ann, off = {}, 0
+    for n, s in zip(names, g["ann_sizes"]):
+        ann[n] = pts[off:off + int(s)]
+        off += int(s)
+    return feats, ann, tuple(int(v) for v in g["vol_shape"])
+
+
+def test_prototype_sampling_matches_reference(golden):
+    g = golden("sim_refntf")
+    feats, ann, vs = _sim_inputs(g)
+    pts = torch.cat(list(ann.values()))
+    rel = osim.rel_coords(pts, vs)
+    assert torch.allclose(osim.sample_prototypes(feats, rel, "bilinear"), torch.from_numpy(g["protos_bilinear"]), atol=1e-6)
+    assert torch.equal(osim.sample_prototypes(feats, rel, "nearest"), torch.from_numpy(g["protos_nearest"]))
+    # P1 (tests/test_vishum.py:17-23): nearest sample at a voxel centre == direct index
+    s = [vs[i] // feats.shape[1 + i] for i in range(3)]
+    direct = torch.stack([feats[:, p[0] // s[0], p[1] // s[1], p[2] // s[2]] for p in pts.tolist()])
+    assert torch.equal(osim.sample_prototypes(feats, rel, "nearest"), direct)
+
+
+def test_ref_ntf_matches_reference(golden):
+    g = golden("sim_refntf")
+    feats, ann, vs = _sim_inputs(g)
+    out = osim.ref_ntf(vs, feats, ann)
+    for n, v in out.items():
+        ref = torch.from_numpy(g[f"sim_{n}"])
+        assert v.dtype == torch.uint8 and v.shape == ref.shape
+        d = (v.int() - ref.int()).abs()
+        assert (d > 1).float().mean() < 1e-3, n          # float reassociation may flip a quantisation step
+
+
+def test_ns_slabbed_equals_direct():
+    feats, protos = synth.class_features(24, (6, 5, 4), 3, seed=2, dtype=torch.float32)
+    p = torch.cat([protos, protos.flip(0)])
+    offs = [0, 2, 4, 6]
+    a = osim.ns_composite(feats, p, offs, (24, 15, 20), slab=3)
+    b = osim.ns_composite_direct(feats, p, offs, (24, 15, 20))
+    assert torch.allclose(a, b, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["bls_s755", "bls_s333", "bls_default"])
+def test_bls_matches_reference(golden, name):
+    g = golden(name)
+    shape = tuple(int(v) for v in g["shape"])
+    ss, sl, sc = [int(v) for v in g["sig"]]
+    gp = dict(sigma_spatial=ss, sigma_luma=sl, sigma_chroma=sc)
+    r8, lab = synth.ct_volume(shape, n_shells=4, seed=7)
+    gen = torch.Generator().manual_seed(11)
+    t = ((lab == 1).float() * 0.8 + 0.2 * torch.rand(shape, generator=gen)).clamp(0, 1)
+    cexp = torch.rand((1,) + shape, generator=gen)
+    r3 = r8.expand(3, -1, -1, -1)
+    sp, nvert = bls.solve_sparse(t[None], r3, grid_params=gp)
+    de, info = bls.solve_dense(t[None], r3, grid_params=gp, return_info=True)
+    ref = torch.from_numpy(g["out"])
+    assert info["nvert"] == nvert
+    assert (sp - ref).abs().max() < 1e-6
+    assert (de - ref).abs().max() < 1e-6
+    de_c = bls.solve_dense(t[None], r3, c=cexp, grid_params=gp)
+    assert (de_c - torch.from_numpy(g["out_c"])).abs().max() < 1e-6
+
+
+def test_crop_helpers_match_reference(golden):
+    g = golden("crop")
+    s = torch.from_numpy(g["s"])
+    crops, (lo, hi) = bls.crop_pad([s, s[0] * 2], thresh=0.1, pad=2)
+    assert np.array_equal(lo.numpy(), g["mi"]) and np.array_equal(hi.numpy(), g["ma"])
+    assert torch.equal(crops[0], torch.from_numpy(g["c0"])) and torch.equal(crops[1], torch.from_numpy(g["c1"]))
+    # P2 (tests/test_bls_crop.py:49-55): crop -> write back reproduces the region
+    full = torch.zeros_like(s)
+    bls.write_crop_into(full, crops[0], (lo, hi))
+    assert torch.equal(full[..., lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]], crops[0])
+
+
+def test_luma_lut_is_not_floor_division():
+    lut = bls.luma_lut(5)
+    assert (lut != np.arange(256) // 5).sum() == 9
