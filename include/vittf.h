@@ -1,0 +1,191 @@
+/* libvittf_b200 -- C ABI of the B200-native vit-tf feature-volume hot path.
+ *
+ * The reference (xeTaiz/vit-tf) is pure Python and has no FFI layer of its own; the
+ * boundary it exposes for this path is a set of Python functions.  Each
+ * entry point below names the reference interface (file:line under /root/reference) whose
+ * arithmetic it replaces; the modules in vittf_b200/ keep the Python signatures and call these through
+ * ctypes (see INTEGRATION.md for the binding a maintainer would add to the reference).
+ *
+ * Conventions
+ *   - every function returns VITTF_OK (0) or a negative vittf_status; the message of the
+ *     last failure on the calling thread is available from vittf_last_error();
+ *   - all pointers are DEVICE pointers owned by the caller (torch allocator) unless the
+ *     parameter name ends in _host; nothing is allocated behind the caller's back except
+ *     inside an explicit context object (vittf_vit_create / vittf_bls_create);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *   - volumes are C-contiguous (X, Y, Z) with Z fastest, feature volumes (F, fX, fY, fZ),
+ *     exactly the layouts of the reference's tensors.
+ */
+#ifndef VITTF_H
+#define VITTF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    VITTF_OK = 0,
+    VITTF_ERR_INVALID = -1, /* bad argument / unsupported shape */
+    VITTF_ERR_CUDA = -2,    /* a CUDA runtime/driver call failed */
+    VITTF_ERR_NOMEM = -3,   /* workspace too small */
+    VITTF_ERR_STATE = -4    /* context used before it was fully initialised */
+} vittf_status;
+
+typedef enum { VITTF_U8 = 0, VITTF_F16 = 1, VITTF_BF16 = 2, VITTF_F32 = 3, VITTF_F64 = 4 } vittf_dtype;
+
+const char* vittf_last_error(void);
+int vittf_version(void);
+/* compute capability of the current device, major*10+minor (100 on B200) */
+int vittf_device_arch(int* out_arch);
+
+/* =====================================================================================
+ * Stage 1 -- ViT K-feature extraction (infer.py:130-210 compute_qkv, :314-340 main loop)
+ * ===================================================================================== */
+
+/* Global intensity range of the volume: norm_minmax, infer.py:32-34 (used at :155).
+ * out2 = {min, max} as float32. */
+int vittf_minmax(const void* vol, int64_t n, int dtype, float* out2, void* stream);
+
+typedef struct {
+    int embed_dim;   /* D: 384 (ViT-S) / 768 (ViT-B) */
+    int depth;       /* L: number of blocks of the hub model (12); the last block only
+                        contributes norm1 + the K third of attn.qkv */
+    int num_heads;   /* 6 / 12, head dim must be 64 */
+    int patch;       /* 8 or 16 */
+    int mlp_hidden;  /* 4*D */
+} vittf_vit_config;
+
+/* Device pointers to the weights of one transformer block, PyTorch Linear layout
+ * (out_features, in_features), bf16 matrices, fp32 vectors. */
+typedef struct {
+    const float* ln1_w; const float* ln1_b;
+    const void* qkv_w;  const float* qkv_b;   /* (3D, D) */
+    const void* proj_w; const float* proj_b;  /* (D, D)  */
+    const float* ln2_w; const float* ln2_b;
+    const void* fc1_w;  const float* fc1_b;   /* (4D, D) */
+    const void* fc2_w;  const float* fc2_b;   /* (D, 4D) */
+} vittf_block_weights;
+
+typedef struct vittf_vit vittf_vit; /* opaque */
+
+/* Creates the engine: replaces `model = dino_model_fn(...).to(dev).eval()` (infer.py:323)
+ * as far as the hooked output is concerned.
+ *   patch_w   fp32 (p*p, D), tap-major: patch-embed conv weight with the 3 identical grey
+ *             channels and the ImageNet mean/std affine folded in,
+ *             patch_b fp32 (D)
+ *   max_batch largest number of slices per forward; workspace is caller-provided.       */
+int vittf_vit_create(vittf_vit** out, const vittf_vit_config* cfg, const vittf_block_weights* blocks_host,
+                     const float* patch_w, const float* patch_b, int max_batch, int max_tokens);
+void vittf_vit_destroy(vittf_vit* v);
+/* bytes of scratch the engine needs for `batch` images of `tokens` tokens (incl. CLS) */
+int64_t vittf_vit_workspace_bytes(const vittf_vit* v, int batch, int tokens);
+
+/* One forward over slices [s0, s1) of `vol` along `axis` (0='x',1='y',2='z'):
+ * slicing + min-max + NN resize (infer.py:137-155,177) -> patch embed + cls/pos -> L-1 blocks
+ * -> norm1 + K projection of the last block -> fp16 K features of the PATCH tokens,
+ * out_k (s1-s0, f0*f1, D) with D fastest (what infer.py:201-202 extracts from the hook).
+ *   pos_embed fp32 (1+f0*f1, D) already interpolated for this image size (hub
+ *             interpolate_pos_encoding), row 0 = cls_token + pos[0].
+ *   im0, im1  network input size for this axis (image_sizes, infer.py:143-147).           */
+int vittf_vit_k_features(vittf_vit* v, const void* vol, int vol_dtype, int X, int Y, int Z, int axis, int s0, int s1,
+                         int im0, int im1, const float* minmax2, const float* pos_embed, void* out_k_f16,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* AdaptiveAvgPool3d along the slice axis only + permute to the reference's (D,fX,fY,fZ)
+ * layout (infer.py:203 with pool_fn from :329): k (S, f0*f1, D) fp16 -> out fp16.
+ * n_out == S reproduces the `_noop` pool of single-axis runs (infer.py:326).
+ * accumulate != 0 adds (in fp16, rounding like infer.py:332) into `out` instead of storing. */
+int vittf_pool_axis(const void* k_f16, int S, int f0, int f1, int D, int axis, int n_out, void* out_f16,
+                    int accumulate, void* stream);
+
+/* -------- individually exported building blocks (unit-tested against torch) ---------- */
+enum { VITTF_EPI_BIAS_BF16 = 0, VITTF_EPI_BIAS_GELU_BF16 = 1, VITTF_EPI_BIAS_RESID_F32 = 2,
+       VITTF_EPI_QKV_SPLIT = 3, VITTF_EPI_KFEAT_F16 = 4 };
+/* C[M,N] = A[M,K] (bf16, row-major) x W[N,K]^T (bf16) + bias, tcgen05/TMEM/TMA.
+ *   epi 0/1: out bf16 (M,N) [GELU(erf) for 1];  epi 2: out fp32 (M,N) += (residual stream);
+ *   epi 3: N = 3D, out = qk bf16 (M, 2D), out2 = V^T bf16 (B*heads*64, tok_pad) with
+ *          tokens/tok_pad describing the (image, token) split of M;
+ *   epi 4: out fp16 ((M/tokens)*(tokens-1), N): CLS rows dropped (K features).             */
+int vittf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, void* out2, int M, int N, int K,
+                    int epi, int tokens, int tok_pad, void* stream);
+/* softmax(Q K^T / 8) V per (image, head); qk (B*tokens, 2D) bf16, vt as written by epi 3,
+ * out bf16 (B*tokens, D). */
+int vittf_attention(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads, void* stream);
+/* LayerNorm(eps=1e-6) over the last dim: x fp32 (rows, D) -> y bf16 */
+int vittf_layernorm(const float* x, const float* w, const float* b, void* y_bf16, int64_t rows, int D, void* stream);
+/* slices -> tokens fp32 (B, 1+f0*f1, D) incl. cls/pos (see vittf_vit_k_features) */
+int vittf_patch_embed(const void* vol, int vol_dtype, int X, int Y, int Z, int axis, int s0, int s1, int im0, int im1,
+                      int patch, int D, const float* minmax2, const float* patch_w, const float* patch_b,
+                      const float* pos_embed, float* out_tokens, void* stream);
+
+/* =====================================================================================
+ * Stage 2 -- prototype similarity (predict_ntf.py:24-101, old/cluster_dino.py:306-345)
+ * ===================================================================================== */
+
+/* sample_features3d (infer.py:48-72): grid_sample with align_corners=False, zero padding.
+ *   feats (F,w,h,d) fp16|fp32, rel (A,3) fp32 in [-1,1] (X,Y,Z order), mode 0 nearest /
+ *   1 trilinear ('bilinear'), out fp32 (A,F). */
+int vittf_sample_prototypes(const void* feats, int feat_dtype, int F, int w, int h, int d, const float* rel, int A,
+                            int mode, float* out, void* stream);
+
+/* Low-resolution pass: reads the feature volume ONCE and produces
+ *   dots  fp32 (A, n_lr)   <f_v, p_a>         (einsum 'fwhd,caf->cawhd', predict_ntf.py:65)
+ *   gram  fp32 (14, n_lr)  <f_v, f_{v+o}> for o in {0} U 13 forward neighbours (may be
+ *                             NULL): lets the up-sampling pass evaluate |interp(f)|^2
+ *                             without materialising interp(f).         */
+int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w, int h, int d, const float* protos, int A,
+                     float* dots, float* gram, void* stream);
+
+typedef enum {
+    VITTF_SIM_NS = 0,     /* interp(features) -> L2 normalise -> dot -> clamp(0,1)^e -> class MAX */
+    VITTF_SIM_REFNTF = 1, /* raw dot -> where(>=thr)^e -> class MEAN           (predict_ntf.py:71-72) */
+    VITTF_SIM_LEGACY = 2  /* normalise at low res -> dot -> clamp(0,1)^e -> MAX (cluster_dino.py:307-322) */
+} vittf_sim_mode;
+
+/* Second pass: per OUTPUT voxel combine the 8 surrounding low-res dots (trilinear,
+ * align_corners=False index rule of F.interpolate), normalise, non-linearity, per-class
+ * reduction.  Output z-range [z0,z1) of the (W,H,D) grid only (z-slab sharding, §8e):
+ * out fp32 (C, W, H, z1-z0).  For REFNTF/LEGACY the output grid equals the low-res grid.
+ *   class_offsets int32 (C+1) prefix offsets into the A prototypes.                        */
+int vittf_sim_upsample(const float* dots, const float* gram, int w, int h, int d, int A, const int* class_offsets,
+                       int C, int W, int H, int D, int z0, int z1, int mode, float threshold, float exponent,
+                       float* out, void* stream);
+
+/* 0.99*max quantisation input (predict_ntf.py:95): per-class maximum, out fp32 (C) */
+int vittf_class_max(const float* sims, int C, int64_t n, float* out, void* stream);
+/* label composition (predict_ntf.py:203-215): thresholded running arg-max with strict '>'
+ * on uint8 maps; thresholds_u8[i] = int(thr_i*255).  mode 1 = plain argmax(0) of float maps
+ * (old/cluster_dino.py:345), writing int32 in that case is avoided: labels are uint8.      */
+int vittf_labels(const void* sims, int sims_dtype, int C, int64_t n, const int* thresholds_u8, int mode,
+                 uint8_t* out, void* stream);
+
+/* =====================================================================================
+ * Stage 3 -- 3-D bilateral solver (bilateral_solver3d.py:211-245)
+ * ===================================================================================== */
+typedef struct {
+    int W, H, D;             /* shape of t / r[0] (crop-local) */
+    double sigma_spatial;    /* grid_params, bilateral_solver3d.py:156-160 */
+    double lam, A_diag_min, cg_tol; /* bs_params, :162-167 */
+    int cg_maxiter;
+    int luma_bins;           /* max(lut)+1 */
+} vittf_bls_params;
+
+/* bytes of fp64 grid scratch needed */
+int64_t vittf_bls_workspace_bytes(const vittf_bls_params* p, int nrhs);
+/* Solves `nrhs` targets that share one reference volume.
+ *   t fp32 (nrhs,W,H,D) targets; r_u8 (W,H,D) grey reference; conf fp32 (W,H,D) or NULL for
+ *   the Sobel confidence (:176-181,233-237); luma_lut int32[256] from the reference's exact
+ *   numpy expression; out fp32 (nrhs,W,H,D); iters_out int32 (nrhs) PCG
+ *   iterations actually run (device pointer, may be NULL).                                   */
+int vittf_bls_solve(const vittf_bls_params* p, const float* t, const uint8_t* r_u8, const float* conf,
+                    const int* luma_lut, int nrhs, float* out, int* iters_out, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+/* Sobel confidence alone: out fp32 (W,H,D) = max(c) - c (needs a float scratch of 1 elem) */
+int vittf_sobel_confidence(const uint8_t* r_u8, int W, int H, int D, float* out, float* scratch_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITTF_H */

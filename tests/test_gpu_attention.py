@@ -1,0 +1,27 @@
+"""tcgen05 flash attention (vittf_attention) against torch softmax(QK^T/8)V in fp32."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,tokens,heads,scale", [(1, 65, 6, 1.0), (2, 129, 6, 1.0), (2, 300, 6, 3.0), (1, 1025, 12, 1.0),
+                                                   (2, 4097, 6, 1.0), (1, 4097, 6, 6.0)])
+def test_attention_matches_torch(B, tokens, heads, scale):
+    from vittf_b200 import ops
+    D = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(tokens + heads)
+    qkv = (torch.randn(B, tokens, 3, heads, 64, device="cuda", generator=g) * scale).bfloat16()
+    qk = qkv[:, :, :2].reshape(B * tokens, 2 * D).contiguous()
+    tok_pad = ops.tok_pad_of(tokens)
+    vt = torch.zeros(B, D, tok_pad, dtype=torch.bfloat16, device="cuda")
+    vt[:, :, :tokens] = qkv[:, :, 2].reshape(B, tokens, D).permute(0, 2, 1)
+    out = ops.attention(qk, vt.view(B * D, tok_pad), B, tokens, heads, tok_pad)
+    q, k, v = [qkv[:, :, i].permute(0, 2, 1, 3).float() for i in range(3)]
+    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1) @ v                  # (B, h, N, 64)
+    ref = att.permute(0, 2, 1, 3).reshape(B * tokens, D)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+    cos = torch.nn.functional.cosine_similarity(out.float(), ref, dim=-1).min().item()
+    assert cos > 0.999, cos

@@ -1,0 +1,77 @@
+"""tcgen05 GEMM epilogues (vittf_gemm_bf16) against torch on the same bf16-rounded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(M, N, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    return a, w, b
+
+
+def _ref(a, w, b):
+    return a.float() @ w.float().t() + b
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 384, 384), (4097 * 2, 1536, 384), (1000, 384, 1536), (131, 768, 768)])
+def test_gemm_bias_bf16(M, N, K):
+    from vittf_b200 import _lib, ops
+    a, w, b = _mk(M, N, K)
+    out = ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_BF16)
+    ref = _ref(a, w, b)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_gemm_gelu():
+    from vittf_b200 import _lib, ops
+    a, w, b = _mk(513, 1536, 384, seed=1)
+    out = ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_GELU_BF16)
+    ref = torch.nn.functional.gelu(_ref(a, w, b))
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+def test_gemm_residual_fp32():
+    from vittf_b200 import _lib, ops
+    a, w, b = _mk(777, 384, 1536, seed=2)
+    x = torch.randn(777, 384, device="cuda")
+    ref = x + _ref(a, w, b)
+    ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_RESID_F32, out=x)
+    assert (x - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("tokens,B", [(65, 3), (4097, 2)])
+def test_gemm_qkv_split(tokens, B):
+    from vittf_b200 import _lib, ops
+    D, heads = 384, 6
+    a, w, b = _mk(B * tokens, 3 * D, D, seed=3)
+    tok_pad = ops.tok_pad_of(tokens)
+    qk, vt = ops.gemm_bf16(a, w, b, _lib.EPI_QKV_SPLIT, tokens=tokens, tok_pad=tok_pad)
+    ref = _ref(a, w, b)
+    assert (qk.float() - ref[:, :2 * D]).abs().max().item() < 2e-2
+    v_ref = ref[:, 2 * D:].view(B, tokens, heads * 64).permute(0, 2, 1)          # (B, heads*64, tokens)
+    vt = vt.view(B, heads * 64, tok_pad)
+    assert (vt[:, :, :tokens].float() - v_ref).abs().max().item() < 2e-2
+    assert vt[:, :, tokens:].abs().max().item() == 0
+
+
+def test_gemm_kfeat_drops_cls():
+    from vittf_b200 import _lib, ops
+    tokens, B, D = 65, 4, 384
+    a, w, b = _mk(B * tokens, D, D, seed=4)
+    out = ops.gemm_bf16(a, w, b, _lib.EPI_KFEAT_F16, tokens=tokens)
+    ref = _ref(a, w, b).view(B, tokens, D)[:, 1:].reshape(-1, D)
+    assert out.dtype == torch.float16 and out.shape == ref.shape
+    assert (out.float() - ref).abs().max().item() < 5e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_rejects_bad_shapes():
+    from vittf_b200 import _lib, ops
+    a, w, b = _mk(64, 100, 64)
+    with pytest.raises(_lib.VittfError):
+        ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_BF16)

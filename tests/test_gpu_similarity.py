@@ -1,0 +1,130 @@
+"""Stage 2 on the GPU against the golden vectors of the reference's own predict_ntf / infer code and
+against the oracle (tolerance from north_star: similarity maps within 2e-3 absolute; labels >= 99.9 %
+agreement and exact where the top-2 margin exceeds 1e-2)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def _sim_inputs(g):
+    feats = torch.from_numpy(g["feats"])
+    pts = torch.from_numpy(g["ann_pts"])
+    ann, off = {}, 0
+    for n, s in zip([str(n) for n in g["ann_names"]], g["ann_sizes"]):
+        ann[n] = pts[off:off + int(s)]
+        off += int(s)
+    return feats, ann, tuple(int(v) for v in g["vol_shape"])
+
+
+def test_sample_features3d_matches_reference(golden):
+    from vittf_b200 import infer
+    from oracle import similarity as osim
+    g = golden("sim_refntf")
+    feats, ann, vs = _sim_inputs(g)
+    rel = osim.rel_coords(torch.cat(list(ann.values())), vs)
+    for mode, key in (("bilinear", "protos_bilinear"), ("nearest", "protos_nearest")):
+        out = infer.sample_features3d(feats.cuda(), rel.clone(), mode=mode)
+        assert out.shape == (1, 1, rel.shape[0], feats.shape[0]) and out.is_cuda
+        assert (out[0, 0].cpu() - torch.from_numpy(g[key])).abs().max().item() < 1e-6
+    # CPU tensors are accepted too (result comes back on the CPU), fp16 features as in `--gpu` mode
+    out16 = infer.sample_features3d(feats.half(), rel.clone(), mode="nearest")
+    assert not out16.is_cuda and out16.dtype == torch.float16
+    assert torch.equal(out16[0, 0], torch.from_numpy(g["protos_nearest"]).half())
+
+
+def test_compute_similarities_matches_reference(golden):
+    from vittf_b200 import predict_ntf
+    g = golden("sim_refntf")
+    feats, ann, vs = _sim_inputs(g)
+    import numpy as np
+    out = predict_ntf.compute_similarities(np.zeros(vs, np.float32), feats.cuda(), ann, bilateral_solver=False)
+    assert list(out.keys()) == list(ann.keys())
+    for n, v in out.items():
+        ref = torch.from_numpy(g[f"sim_{n}"])
+        assert v.dtype == torch.uint8 and v.shape == ref.shape and not v.is_cuda
+        d = (v.int() - ref.int()).abs()
+        assert (d > 1).float().mean().item() < 1e-3, n          # one quantisation step from float reassociation
+    assert predict_ntf.compute_similarities(np.zeros(vs, np.float32), feats.cuda(), {}) is None
+
+
+def test_refntf_float_matches_oracle(golden):
+    from oracle import similarity as osim
+    from vittf_b200 import predict_ntf
+    g = golden("sim_refntf")
+    feats, ann, vs = _sim_inputs(g)
+    ref = torch.stack(list(osim.ref_ntf_float(vs, feats, ann).values()))
+    out = predict_ntf.similarity_float(vs, feats.cuda(), ann).cpu()
+    assert (out - ref).abs().max().item() < TOL
+
+
+def test_compute_similarities_with_bilateral_solver(golden):
+    import numpy as np
+    from oracle import synth
+    from vittf_b200 import predict_ntf
+    g = golden("sim_refntf")
+    gb = golden("sim_refntf_bls")
+    feats, ann, vs = _sim_inputs(g)
+    vol_u8, _ = synth.ct_volume(vs, n_shells=3, seed=5)
+    out = predict_ntf.compute_similarities(vol_u8.float().numpy(), feats.cuda(), ann, bilateral_solver=True)
+    for n, v in out.items():
+        ref = torch.from_numpy(gb[f"sim_{n}"])
+        assert v.shape == ref.shape and v.dtype == torch.uint8
+        d = (v.int() - ref.int()).abs()
+        d = torch.minimum(d, 256 - d)                           # the reference's uint8 cast wraps above 255
+        assert (d > 1).float().mean().item() < 2e-3, (n, d.max().item())
+
+
+@pytest.mark.parametrize("lr,out_shape,F_,A", [((6, 5, 4), (24, 15, 20), 24, 6), ((16, 16, 16), (64, 64, 64), 96, 8),
+                                               ((8, 8, 8), (8, 8, 8), 32, 3), ((12, 10, 8), (31, 29, 17), 40, 20)])
+def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
+    from oracle import similarity as osim, synth
+    from vittf_b200.similarity import similarity_maps
+    C = min(A, 3)
+    feats, protos = synth.class_features(F_, lr, C, seed=2, dtype=torch.float16)
+    g = torch.Generator().manual_seed(9)
+    p = F.normalize(protos.repeat((A + C - 1) // C, 1)[:A] + 0.05 * torch.randn(A, F_, generator=g), dim=-1)
+    offs = [round(i * A / C) for i in range(C + 1)]
+    ref = osim.ns_composite(feats, p, offs, out_shape, exponent=2.0, slab=5)
+    out = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
+                          out_shape, mode="ns", exponent=2.0).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() < TOL
+    # z-slab evaluation (multi-GPU sharding unit) gives the same voxels
+    zs = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
+                         out_shape, mode="ns", exponent=2.0, z_range=(3, out_shape[2] - 2)).cpu()
+    assert torch.equal(zs, out[..., 3:out_shape[2] - 2])
+    # labels: >= 99.9 % agreement, exact where the top-2 margin exceeds 1e-2
+    from vittf_b200.predict_ntf import argmax_labels
+    lab = argmax_labels(out.cuda()).cpu().long()
+    ref_lab = osim.argmax_labels(ref)
+    top2 = ref.topk(2, dim=0).values
+    margin = top2[0] - top2[1]
+    assert (lab == ref_lab).float().mean().item() >= 0.999
+    assert torch.equal(lab[margin > 1e-2], ref_lab[margin > 1e-2])
+
+
+def test_legacy_similarity_matches_oracle():
+    from oracle import similarity as osim, synth
+    from vittf_b200 import infer
+    from vittf_b200.similarity import class_offsets, rel_coords, similarity_maps
+    vs, lr = (48, 40, 32), (12, 10, 8)
+    feats, _ = synth.class_features(32, lr, 3, seed=5, dtype=torch.float32)
+    ann = synth.annotations(vs, 3, 5, seed=5)
+    ref = torch.stack(list(osim.legacy(feats, ann, vs).values()))
+    fc = feats.cuda()
+    rel = rel_coords(torch.cat(list(ann.values())), vs, fc.device)
+    protos = F.normalize(infer.sample_features3d(fc, rel, mode="nearest")[0, 0], dim=-1).contiguous()
+    out = similarity_maps(fc, protos, class_offsets(ann, fc.device), mode="legacy", exponent=2.0).cpu()
+    assert (out - ref).abs().max().item() < TOL
+
+
+def test_compose_labels_matches_oracle():
+    from oracle import similarity as osim
+    from vittf_b200.predict_ntf import compose_labels
+    g = torch.Generator().manual_seed(4)
+    sims = (torch.rand(5, 20, 18, 16, generator=g) * 255).to(torch.uint8)
+    thr = [0.486, 0.264, 0.236, 0.68, 0.291]                   # predict_ntf.py:208
+    assert torch.equal(compose_labels(sims, thr), osim.compose_labels(sims, thr))

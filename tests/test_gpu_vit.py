@@ -1,0 +1,125 @@
+"""Stage 1 on the GPU: streaming kernels, the engine, and the feature volume against the oracle and
+the golden vectors produced by the reference's own infer.py (tolerance from north_star:
+cosine >= 0.995 per patch vs the fp32 reference)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_targets_this_gpu():
+    from vittf_b200 import ops
+    assert ops.device_arch() == 100, "libvittf_b200 is built for sm_100a (B200) only"
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float16, torch.float32])
+def test_minmax(dtype):
+    from vittf_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    v = (torch.rand(37, 41, 43, generator=g) * 200 - (0 if dtype == torch.uint8 else 50)).to(dtype).cuda()
+    mm = ops.minmax(v)
+    assert mm[0].item() == v.float().min().item() and mm[1].item() == v.float().max().item()
+
+
+@pytest.mark.parametrize("D", [384, 768])
+def test_layernorm(D):
+    from vittf_b200 import ops
+    x = torch.randn(1001, D, device="cuda") * 3 + 1
+    w, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    ref = F.layer_norm(x, (D,), w, b, eps=1e-6)
+    assert (ops.layernorm(x, w, b).float() - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("axis", ["z", "y", "x"])
+@pytest.mark.parametrize("shape,n_out", [((8, 4, 6), 4), ((7, 4, 6), 3), ((6, 4, 6), 6)])
+def test_pool_axis_matches_adaptive_avg_pool(axis, shape, n_out):
+    from vittf_b200 import ops
+    S, f0, f1 = shape
+    D = 64
+    k = torch.randn(S, f0 * f1, D, device="cuda").half()
+    out = ops.pool_axis(k, f0, f1, axis, n_out)
+    kk = k.view(S, f0, f1, D)
+    perm = {"z": (3, 1, 2, 0), "y": (3, 1, 0, 2), "x": (3, 0, 1, 2)}[axis]
+    unpooled = kk.permute(*perm).float()
+    tgt = {"z": (f0, f1, n_out), "y": (f0, n_out, f1), "x": (n_out, f0, f1)}[axis]
+    ref = F.adaptive_avg_pool3d(unpooled, tgt).half()
+    assert torch.equal(out, ref)
+    acc = ops.pool_axis(k, f0, f1, axis, n_out, out=out.clone(), accumulate=True)
+    assert torch.equal(acc, (ref + ref))
+
+
+def _oracle_tokens(model, vol, axis, im_sz):
+    from oracle import feature_volume as fv
+    imgs = fv.slice_images(vol, axis)
+    r, c = fv.AXIS_IMAGE_DIMS[axis]
+    return model.prepare_tokens(F.interpolate(imgs, size=(im_sz[r], im_sz[c]), mode="nearest"))
+
+
+@pytest.mark.parametrize("axis", ["z", "y", "x"])
+def test_patch_embed_matches_prepare_tokens(axis):
+    from oracle import dino_vit, feature_volume as fv, synth
+    from vittf_b200 import ops
+    from vittf_b200.vit import fold_patch_embed, interpolate_pos_embed
+    vol, _ = synth.ct_volume((40, 32, 24), n_shells=4, seed=3)
+    model = dino_vit.build("vits8", depth=1)
+    im_sz, _ = fv.image_sizes(tuple(vol.shape), 8, 8)
+    ref = _oracle_tokens(model, vol, axis, im_sz)
+    r, c = fv.AXIS_IMAGE_DIMS[axis]
+    pw, pb = fold_patch_embed(model.patch_embed.proj.weight, model.patch_embed.proj.bias)
+    pos = interpolate_pos_embed(model.pos_embed, model.cls_token, 8, im_sz[r], im_sz[c])
+    v = vol.cuda()
+    out = ops.patch_embed(v, axis, 0, ref.shape[0], im_sz[r], im_sz[c], 8, ops.minmax(v), pw.cuda(), pb.cuda(), pos.cuda())
+    assert (out.cpu() - ref).abs().max().item() < 1e-4
+
+
+def _cos_min(a, b):
+    a = a.float().flatten(1).t()
+    b = b.float().flatten(1).t()
+    return F.cosine_similarity(a, b, dim=-1).min().item()
+
+
+@pytest.mark.parametrize("name", ["feat_cube", "feat_noncubic"])
+def test_feature_volume_matches_reference_golden(golden, name):
+    from oracle import dino_vit, synth
+    from vittf_b200 import infer
+    g = golden(name)
+    shape, fos, depth = tuple(int(v) for v in g["shape"]), int(g["fos"]), int(g["depth"])
+    vol, _ = synth.ct_volume(shape, n_shells=4, seed=int(g["seed_vol"]))
+    model = dino_vit.build("vits8", seed=int(g["seed_model"]), depth=depth)
+    ref = torch.from_numpy(g["k"])
+    out = infer.feature_volume(vol, model, 8, fos, batch_size=3).cpu()
+    assert out.dtype == torch.float16 and out.shape == ref.shape
+    assert _cos_min(out, ref) >= 0.995
+    # drop-in signature, single axis, un-pooled (infer.py:326)
+    im_sz = tuple(int(v) for v in g["im_sz"])
+    ky = infer.compute_qkv(vol, model, 8, im_sz, batch_size=2, return_keys="k", slice_along="y")["k"]
+    refy = torch.from_numpy(g["k_y_unpooled"])
+    assert ky.shape == refy.shape and ky.dtype == torch.float16 and not ky.is_cuda
+    assert _cos_min(ky, refy) >= 0.995
+    # 3-axis loop through the drop-in exactly as infer.py:327-333 writes it
+    pool = torch.nn.AdaptiveAvgPool3d(tuple(d // 8 for d in im_sz))
+    acc = 0.0
+    for ax in ["z", "y", "x"]:
+        v = infer.compute_qkv(vol, model, 8, im_sz, pool_fn=pool, batch_size=4, return_keys="k", slice_along=ax)["k"]
+        acc = torch.as_tensor(acc) + v.squeeze().half()
+    assert torch.equal(acc, out)
+
+
+def test_vit_full_depth_512(golden):
+    """ViT-S/8, 12 blocks, 512^2 input (4097 tokens, the benchmark shape): two slices vs the fp32 oracle."""
+    from oracle import dino_vit, feature_volume as fv, synth
+    from vittf_b200 import ops
+    from vittf_b200.vit import engine_for
+    model = dino_vit.build("vits8", seed=0)
+    vol, _ = synth.ct_volume((128, 128, 2), n_shells=6, seed=1)
+    imgs = F.interpolate(fv.slice_images(vol, "z"), size=(512, 512), mode="nearest")
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = fv.hooked_qkv(model, imgs)[:, 1:, 384:768].float()                      # (2, 4096, 384)
+    eng = engine_for(model, torch.device("cuda", 0), max_batch=2)
+    v = vol.cuda()
+    out = eng.k_features(v, "z", 0, 2, 512, 512, ops.minmax(v)).float().cpu()
+    cos = F.cosine_similarity(out, ref, dim=-1)
+    assert cos.min().item() >= 0.995, cos.min().item()
+    assert (out - ref).abs().max().item() < 0.05 * ref.abs().max().item()

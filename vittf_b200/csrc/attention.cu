@@ -1,0 +1,278 @@
+// Fused multi-head attention of the DINO ViT blocks (softmax(q k^T * hd^-0.5) v, head dim 64) that
+// /root/reference/infer.py:177 runs through the hub model.  The reference materialises the N x N
+// score matrix per head (N = 4097 at 512^2 input); here it never leaves the SM.
+//
+// B200 design (one CTA per 256 query rows of one (image, head), 384 threads):
+//   warp 0    : TMA producer -- Q tiles once, then a 3-stage ring of K (128x64) and V^T (64x128) tiles
+//   warp 1    : MMA issuer   -- S = Q K^T (tcgen05.mma SS, 128x128x16, fp32 in TMEM), O += P V (tcgen05.mma TS:
+//                               P is read straight from TMEM, V^T from smem), for two query tiles ping-pong
+//   warp 2    : TMEM allocator (S_A, S_B: 2 x 128 cols; O_A, O_B: 2 x 64 cols; P aliases S)
+//   warps 4-7 : softmax of query tile A, one score row per thread (tcgen05.ld 32x32b), online max with lazy
+//   warps 8-11: softmax of query tile B  rescaling of O (only when the row max grows by > 2^8), P written back
+//                                         to TMEM as packed bf16.
+// The tensor pipe works on tile B while the CUDA cores do the exponentials of tile A and vice versa.
+#include "common.cuh"
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int KV_STAGES = 3;
+constexpr int ATT_THREADS = 384;
+constexpr int Q_TILE_BYTES = BQ * HD * 2;        // 16 KB
+constexpr int K_TILE_BYTES = BKV * HD * 2;       // 16 KB
+constexpr int V_HALF_BYTES = HD * 64 * 2;        // 8 KB: 64 d-rows x 64 keys
+constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;
+constexpr int ATT_SMEM_BYTES = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 512;
+constexpr int COL_S = 0;     // + t*128
+constexpr int COL_O = 256;   // + t*64
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct AttnParams {
+    __nv_bfloat16* out;
+    int tokens, heads, D;
+    float scale_log2e;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+    attention_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_q = smem;
+    uint8_t* s_kv = smem + 2 * Q_TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + KV_STAGES * KV_STAGE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + KV_STAGES;
+    uint64_t* s_full = kv_empty + KV_STAGES;  // [2]
+    uint64_t* p_ready = s_full + 2;           // [2]
+    uint64_t* o_final = p_ready + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+    const int q0 = unit * 2 * BQ;
+    const bool has_b = q0 + BQ < p.tokens;
+    const int n_tiles = has_b ? 2 : 1;
+    const int nkv = (p.tokens + BKV - 1) / BKV;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(q_full, 1);
+        for (int i = 0; i < KV_STAGES; ++i) {
+            ptx::mbar_init(&kv_full[i], 1);
+            ptx::mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&s_full[i], 1);
+            ptx::mbar_init(&p_ready[i], 128);
+        }
+        ptx::mbar_init(o_final, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (threadIdx.x == 0) {
+        // ---------------- TMA producer ----------------
+        ptx::prefetch_tmap(&tm_qk);
+        ptx::prefetch_tmap(&tm_vt);
+        ptx::mbar_arrive_expect_tx(q_full, n_tiles * Q_TILE_BYTES);
+        for (int t = 0; t < n_tiles; ++t)
+            ptx::tma_load_3d(s_q + t * Q_TILE_BYTES, &tm_qk, q_full, head * HD, q0 + t * BQ, img);
+        const int vt_row = (img * p.heads + head) * HD;
+        for (int j = 0; j < nkv; ++j) {
+            const int st = j % KV_STAGES;
+            ptx::mbar_wait(&kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+            uint8_t* dst = s_kv + st * KV_STAGE_BYTES;
+            ptx::mbar_arrive_expect_tx(&kv_full[st], KV_STAGE_BYTES);
+            ptx::tma_load_3d(dst, &tm_qk, &kv_full[st], p.D + head * HD, j * BKV, img);
+            ptx::tma_load_2d(dst + K_TILE_BYTES, &tm_vt, &kv_full[st], j * BKV, vt_row);
+            ptx::tma_load_2d(dst + K_TILE_BYTES + V_HALF_BYTES, &tm_vt, &kv_full[st], j * BKV + 64, vt_row);
+        }
+    } else if (threadIdx.x == 32) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BQ, BKV);
+        constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, HD);
+        const uint32_t q_addr = ptx::smem_u32(s_q);
+        const uint32_t kv_addr = ptx::smem_u32(s_kv);
+        auto issue_s = [&](int t, int st) {
+            const uint64_t adesc = ptx::smem_desc_k_sw128(q_addr + t * Q_TILE_BYTES);
+            const uint64_t bdesc = ptx::smem_desc_k_sw128(kv_addr + st * KV_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k)
+                ptx::umma_ss(tmem_base + COL_S + t * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        };
+        auto issue_pv = [&](int t, int st, bool acc) {
+            const uint32_t v_addr = kv_addr + st * KV_STAGE_BYTES + K_TILE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BKV / 16; ++ks) {
+                const uint64_t bdesc = ptx::smem_desc_k_sw128(v_addr + (ks >> 2) * V_HALF_BYTES) + 2 * (ks & 3);
+                // P: packed bf16 pairs, 8 TMEM columns per 16 keys
+                ptx::umma_ts(tmem_base + COL_O + t * 64, tmem_base + COL_S + t * 128 + ks * 8, bdesc, idesc_o,
+                             acc || ks != 0);
+            }
+        };
+        ptx::mbar_wait(q_full, 0);
+        ptx::mbar_wait(&kv_full[0], 0);
+        ptx::tc_fence_after();
+        for (int t = 0; t < n_tiles; ++t) {
+            issue_s(t, 0);
+            ptx::tc_commit(&s_full[t]);
+        }
+        for (int j = 0; j < nkv; ++j) {
+            const int st = j % KV_STAGES;
+            const bool more = j + 1 < nkv;
+            if (more) {
+                ptx::mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
+                ptx::tc_fence_after();
+            }
+            for (int t = 0; t < n_tiles; ++t) {
+                ptx::mbar_wait(&p_ready[t], j & 1);
+                ptx::tc_fence_after();
+                issue_pv(t, st, j > 0);
+                if (more) {
+                    issue_s(t, (j + 1) % KV_STAGES);
+                    ptx::tc_commit(&s_full[t]);  // also certifies that P V of block j is complete
+                }
+            }
+            ptx::tc_commit(&kv_empty[st]);
+        }
+        ptx::tc_commit(o_final);
+    } else if (warp >= 4) {
+        // ---------------- softmax + output ----------------
+        const int t = (warp - 4) >> 2;
+        if (t < n_tiles) {
+            const int q = warp & 3;
+            const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+            const uint32_t t_s = tmem_base + lane_base + COL_S + t * 128;
+            const uint32_t t_o = tmem_base + lane_base + COL_O + t * 64;
+            const float c = p.scale_log2e;
+            float m_used = -INFINITY;
+            float l = 0.0f;
+            for (int j = 0; j < nkv; ++j) {
+                ptx::mbar_wait(&s_full[t], j & 1);
+                ptx::tc_fence_after();
+                uint32_t s[4][32];
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(t_s + ch * 32, s[ch]);
+                ptx::tc_wait_ld();
+                const int valid = p.tokens - j * BKV;  // >= 1
+                if (valid < BKV) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (ch * 32 + i >= valid) s[ch][i] = 0xff800000u;  // -inf
+                }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[ch][i]));
+                const float m_blk = mx * c;
+                const bool grow = m_blk > m_used + RESCALE_THRESHOLD;
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float m_new = grow ? m_blk : m_used;
+                    const float f = ptx::ex2_approx(m_used - m_new);  // 0 on the first block, 1 if unchanged
+                    if (j > 0) {
+                        uint32_t o[32];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            ptx::tmem_ld32(t_o + h * 32, o);
+                            ptx::tc_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                            ptx::tmem_st32(t_o + h * 32, o);
+                        }
+                    }
+                    l *= f;
+                    m_used = m_new;
+                }
+                float sum = 0.0f;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(s[ch][2 * i]), c, -m_used));
+                        const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(s[ch][2 * i + 1]), c, -m_used));
+                        sum += p0 + p1;
+                        pk[i] = ptx::pack_bf16x2(p0, p1);
+                    }
+                    ptx::tmem_st16(t_s + ch * 16, pk);  // P aliases the first 64 columns of S (row-private)
+                }
+                l += sum;
+                ptx::tc_wait_st();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&p_ready[t]);
+            }
+            // ---- output: O / l -> bf16, token-major (B*tokens, D) at column head*64 ----
+            ptx::mbar_wait(o_final, 0);
+            ptx::tc_fence_after();
+            const int row = q0 + t * BQ + q * 32 + lane;
+            const float inv = 1.0f / l;
+            __nv_bfloat16* dst = p.out + (static_cast<size_t>(img) * p.tokens + row) * p.D + head * HD;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t o[32];
+                ptx::tmem_ld32(t_o + h * 32, o);
+                ptx::tc_wait_ld();
+                if (row < p.tokens) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 pkt;
+                        pkt.x = ptx::pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                        pkt.y = ptx::pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                        pkt.z = ptx::pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                        pkt.w = ptx::pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                        reinterpret_cast<uint4*>(dst + h * 32)[i] = pkt;
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace
+
+extern "C" int vittf_attention(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads,
+                               void* stream) {
+    VITTF_REQUIRE(qk && vt && out, "vittf_attention: null pointer");
+    VITTF_REQUIRE(B > 0 && tokens > 0 && heads > 0, "vittf_attention: empty problem");
+    VITTF_REQUIRE(tok_pad >= tokens && tok_pad % 8 == 0, "vittf_attention: tok_pad=%d must be >= tokens and a multiple of 8",
+                  tok_pad);
+    const int D = heads * HD;
+    CUtensorMap tm_qk, tm_vt;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(2 * D), static_cast<uint64_t>(tokens), static_cast<uint64_t>(B)};
+        uint64_t strides[2] = {static_cast<uint64_t>(2 * D) * 2, static_cast<uint64_t>(2 * D) * 2 * tokens};
+        uint32_t box[3] = {HD, BQ, 1};
+        VITTF_CHECK(vittf_make_tmap(&tm_qk, qk, 2, 3, dims, strides, box, true));
+    }
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(tok_pad), static_cast<uint64_t>(B) * heads * HD};
+        uint64_t strides[1] = {static_cast<uint64_t>(tok_pad) * 2};
+        uint32_t box[2] = {64, HD};
+        VITTF_CHECK(vittf_make_tmap(&tm_vt, vt, 2, 2, dims, strides, box, true));
+    }
+    static bool configured = false;
+    if (!configured) {
+        VITTF_CHECK_CUDA(
+            cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        configured = true;
+    }
+    AttnParams p{static_cast<__nv_bfloat16*>(out), tokens, heads, D, 0.125f * 1.4426950408889634f};
+    dim3 grid(ceil_div(tokens, 2 * BQ), heads, B);
+    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tm_qk, tm_vt, p);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    return VITTF_OK;
+}

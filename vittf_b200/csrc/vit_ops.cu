@@ -1,0 +1,344 @@
+// Streaming kernels around the ViT GEMMs: intensity range, folded patch embedding, LayerNorm,
+// slice-axis average pooling + 3-axis fp16 merge.  All HBM-bound; written for coalesced 128-bit
+// accesses and grids that are multiples of the SM count.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// norm_minmax (infer.py:32-34): global min / max of the volume.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p, int64_t i);
+template <>
+__device__ __forceinline__ float load_as_float<uint8_t>(const uint8_t* p, int64_t i) { return static_cast<float>(p[i]); }
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p, int64_t i) { return __half2float(p[i]); }
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p, int64_t i) { return p[i]; }
+
+__global__ void minmax_init_kernel(float* out2) {
+    out2[0] = INFINITY;
+    out2[1] = -INFINITY;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_kernel(const T* __restrict__ vol, int64_t n, float* out2) {
+    constexpr int VEC = 16 / sizeof(T);
+    float lo = INFINITY, hi = -INFINITY;
+    const int64_t nvec = n / VEC;
+    const uint4* v4 = reinterpret_cast<const uint4*>(vol);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint4 raw = __ldg(v4 + i);
+        const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float f = load_as_float<T>(e, k);
+            lo = fminf(lo, f);
+            hi = fmaxf(hi, f);
+        }
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) {
+            const float f = load_as_float<T>(vol, i);
+            lo = fminf(lo, f);
+            hi = fmaxf(hi, f);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float s_lo[8], s_hi[8];
+    if ((threadIdx.x & 31) == 0) {
+        s_lo[threadIdx.x >> 5] = lo;
+        s_hi[threadIdx.x >> 5] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            lo = fminf(lo, s_lo[w]);
+            hi = fmaxf(hi, s_hi[w]);
+        }
+        atomic_min_float(out2, lo);
+        atomic_max_float(out2 + 1, hi);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch embedding with the input pipeline folded in:
+//   slice -> (v-min)/(max-min) -> 3 identical channels -> ImageNet mean/std -> NN resize -> conv p x p
+// collapses to  token = sum_taps W'[tap][d] * g(src(tap)) + b'[d]  (+ pos-embed), W' = sum_c W_c / std_c.
+// One CTA per (image, patch row); the p*p x f1 gathered grey values live in shared memory.
+// ---------------------------------------------------------------------------------------------
+struct PatchParams {
+    const void* vol;
+    int X, Y, Z, axis, s0;
+    int a, b;          // source image rows / cols for this axis
+    int im0, im1, p, D, f0, f1;
+    const float* minmax;
+    const float* w;    // (p*p, D)
+    const float* bias; // (D)
+    const float* pos;  // (1+f0*f1, D), row 0 already holds cls + pos[0]
+    float* out;        // (B, 1+f0*f1, D)
+};
+
+__device__ __forceinline__ int nearest_src(int dst, int in, int out, float scale) {
+    // ATen nearest (legacy) index rule used by F.interpolate(mode='nearest'), infer.py:177
+    if (in == out) return dst;
+    if (out == 2 * in) return dst >> 1;
+    const int s = static_cast<int>(floorf(dst * scale));
+    return s < in - 1 ? s : in - 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) patch_embed_kernel(PatchParams q) {
+    extern __shared__ float s_g[];  // [f1][p*p]
+    const int img = blockIdx.y;
+    const int py = blockIdx.x;  // == f0 -> CLS row
+    const int ntok = 1 + q.f0 * q.f1;
+    float* out_img = q.out + static_cast<size_t>(img) * ntok * q.D;
+    if (py == q.f0) {
+        for (int d = threadIdx.x; d < q.D; d += blockDim.x) out_img[d] = q.pos[d];
+        return;
+    }
+    const int taps = q.p * q.p;
+    const float lo = q.minmax[0], hi = q.minmax[1];
+    const float inv = 1.0f / (hi - lo);
+    const float sc0 = static_cast<float>(q.a) / static_cast<float>(q.im0);
+    const float sc1 = static_cast<float>(q.b) / static_cast<float>(q.im1);
+    const int s = q.s0 + img;
+    const T* vol = static_cast<const T*>(q.vol);
+    for (int i = threadIdx.x; i < q.f1 * taps; i += blockDim.x) {
+        const int px = i / taps, t = i - px * taps;
+        const int u = t / q.p, v = t - u * q.p;
+        const int r = nearest_src(py * q.p + u, q.a, q.im0, sc0);
+        const int c = nearest_src(px * q.p + v, q.b, q.im1, sc1);
+        int64_t idx;
+        if (q.axis == 2) idx = (static_cast<int64_t>(r) * q.Y + c) * q.Z + s;        // rows X, cols Y
+        else if (q.axis == 1) idx = (static_cast<int64_t>(r) * q.Y + s) * q.Z + c;   // rows X, cols Z
+        else idx = (static_cast<int64_t>(s) * q.Y + r) * q.Z + c;                    // rows Y, cols Z
+        s_g[i] = (load_as_float<T>(vol, idx) - lo) * inv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < q.f1 * q.D; i += blockDim.x) {
+        const int px = i / q.D, d = i - px * q.D;
+        const int tok = 1 + py * q.f1 + px;
+        float acc = q.bias[d] + q.pos[static_cast<size_t>(tok) * q.D + d];
+        const float* g = s_g + px * taps;
+#pragma unroll 8
+        for (int t = 0; t < taps; ++t) acc = fmaf(g[t], __ldg(q.w + static_cast<size_t>(t) * q.D + d), acc);
+        out_img[static_cast<size_t>(tok) * q.D + d] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-6) fp32 -> bf16, one warp per row, row held in registers.
+// ---------------------------------------------------------------------------------------------
+template <int V4>  // float4 per lane: D = 128 * V4
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
+                                                        int64_t rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    constexpr int D = 128 * V4;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[V4];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        v[i] = xr[lane + 32 * i];
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / D);
+    float var = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float a = v[i].x - mean, c = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+        var += (a * a + c * c) + (e * e + f * f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var * (1.0f / D) + 1e-6f);
+    uint2* yr = reinterpret_cast<uint2*>(y + row * D);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+        const float o0 = (v[i].x - mean) * rstd * ww.x + bb.x;
+        const float o1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+        const float o2 = (v[i].z - mean) * rstd * ww.z + bb.z;
+        const float o3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+        yr[lane + 32 * i] = make_uint2(ptx::pack_bf16x2(o0, o1), ptx::pack_bf16x2(o2, o3));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AdaptiveAvgPool3d along the slice axis + permute to (D, fX, fY, fZ) + optional fp16 running sum.
+// k: (S, T = f0*f1, D) fp16, D fastest.  One CTA transposes a 32(token) x 64(d) tile through smem.
+// ---------------------------------------------------------------------------------------------
+struct PoolParams {
+    const __half* k;
+    __half* out;
+    int S, T, D, n_out;
+    int f1;
+    int64_t sd, s0, s1, so;  // output strides (elements) of d, i0, i1, o
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(256) pool_axis_kernel(PoolParams q) {
+    __shared__ float tile[32][65];
+    const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 64, o = blockIdx.z;
+    const int w0 = static_cast<int>((static_cast<int64_t>(o) * q.S) / q.n_out);
+    const int w1 = static_cast<int>((static_cast<int64_t>(o + 1) * q.S + q.n_out - 1) / q.n_out);
+    // load: thread -> (token row = tid/8, 8 halves at d = (tid%8)*8)
+    {
+        const int tr = threadIdx.x >> 3, dc = (threadIdx.x & 7) * 8;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (t0 + tr < q.T && d0 + dc < q.D) {
+            for (int s = w0; s < w1; ++s) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(
+                    q.k + (static_cast<size_t>(s) * q.T + (t0 + tr)) * q.D + d0 + dc));
+                const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h[i]);
+                    acc[2 * i] += f.x;
+                    acc[2 * i + 1] += f.y;
+                }
+            }
+        }
+        const float cnt = static_cast<float>(w1 - w0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[tr][dc + i] = acc[i] / cnt;
+    }
+    __syncthreads();
+    // store: thread -> (d = tid/32 + 8*r, token = tid%32)
+    const int tl = threadIdx.x & 31;
+    const int t = t0 + tl;
+    if (t >= q.T) return;
+    const int i0 = t / q.f1, i1 = t - i0 * q.f1;
+    const int64_t base = i0 * q.s0 + i1 * q.s1 + o * q.so;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int dl = (threadIdx.x >> 5) + 8 * r;
+        if (d0 + dl >= q.D) break;
+        __half* dst = q.out + (d0 + dl) * q.sd + base;
+        const __half pooled = __float2half_rn(tile[tl][dl]);
+        *dst = q.accumulate ? __hadd(*dst, pooled) : pooled;
+    }
+}
+
+}  // namespace
+
+extern "C" int vittf_minmax(const void* vol, int64_t n, int dtype, float* out2, void* stream) {
+    VITTF_REQUIRE(vol && out2 && n > 0, "vittf_minmax: bad arguments");
+    VITTF_REQUIRE((reinterpret_cast<uintptr_t>(vol) & 15) == 0, "vittf_minmax: volume must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    minmax_init_kernel<<<1, 1, 0, s>>>(out2);
+    const int grid = vittf_num_sms() * 8;
+    switch (dtype) {
+        case VITTF_U8: minmax_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(vol), n, out2); break;
+        case VITTF_F16: minmax_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(vol), n, out2); break;
+        case VITTF_F32: minmax_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(vol), n, out2); break;
+        default: VITTF_REQUIRE(false, "vittf_minmax: unsupported dtype %d", dtype);
+    }
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    return VITTF_OK;
+}
+
+extern "C" int vittf_patch_embed(const void* vol, int vol_dtype, int X, int Y, int Z, int axis, int s0, int s1, int im0,
+                                 int im1, int patch, int D, const float* minmax2, const float* patch_w,
+                                 const float* patch_b, const float* pos_embed, float* out_tokens, void* stream) {
+    VITTF_REQUIRE(vol && minmax2 && patch_w && patch_b && pos_embed && out_tokens, "vittf_patch_embed: null pointer");
+    VITTF_REQUIRE(axis >= 0 && axis <= 2, "vittf_patch_embed: axis must be 0 (x), 1 (y) or 2 (z)");
+    const int dims[3] = {X, Y, Z};
+    VITTF_REQUIRE(s0 >= 0 && s1 > s0 && s1 <= dims[axis], "vittf_patch_embed: slice range [%d,%d) outside axis of %d", s0,
+                  s1, dims[axis]);
+    VITTF_REQUIRE(im0 % patch == 0 && im1 % patch == 0 && im0 > 0 && im1 > 0, "vittf_patch_embed: image %dx%d not a multiple of patch %d",
+                  im0, im1, patch);
+    PatchParams q;
+    q.vol = vol; q.X = X; q.Y = Y; q.Z = Z; q.axis = axis; q.s0 = s0;
+    q.a = axis == 0 ? Y : X;
+    q.b = axis == 2 ? Y : Z;
+    q.im0 = im0; q.im1 = im1; q.p = patch; q.D = D; q.f0 = im0 / patch; q.f1 = im1 / patch;
+    q.minmax = minmax2; q.w = patch_w; q.bias = patch_b; q.pos = pos_embed; q.out = out_tokens;
+    const size_t smem = static_cast<size_t>(q.f1) * patch * patch * sizeof(float);
+    VITTF_REQUIRE(smem <= 200 * 1024, "vittf_patch_embed: image row too wide (%zu B of shared memory)", smem);
+    dim3 grid(q.f0 + 1, s1 - s0);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define LAUNCH_PE(T)                                                                                          \
+    do {                                                                                                      \
+        if (smem > 48 * 1024)                                                                                 \
+            VITTF_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  static_cast<int>(smem)));                                  \
+        patch_embed_kernel<T><<<grid, 256, smem, s>>>(q);                                                     \
+    } while (0)
+    switch (vol_dtype) {
+        case VITTF_U8: LAUNCH_PE(uint8_t); break;
+        case VITTF_F16: LAUNCH_PE(__half); break;
+        case VITTF_F32: LAUNCH_PE(float); break;
+        default: VITTF_REQUIRE(false, "vittf_patch_embed: unsupported volume dtype %d", vol_dtype);
+    }
+#undef LAUNCH_PE
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    return VITTF_OK;
+}
+
+extern "C" int vittf_layernorm(const float* x, const float* w, const float* b, void* y_bf16, int64_t rows, int D,
+                               void* stream) {
+    VITTF_REQUIRE(x && w && b && y_bf16 && rows > 0, "vittf_layernorm: bad arguments");
+    VITTF_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, "vittf_layernorm: D=%d must be a multiple of 128 in [128,1024]", D);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, 8));
+    __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
+    switch (D / 128) {
+        case 1: layernorm_kernel<1><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+        case 2: layernorm_kernel<2><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+        case 3: layernorm_kernel<3><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+        case 4: layernorm_kernel<4><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+        case 5: layernorm_kernel<5><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+        case 6: layernorm_kernel<6><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+        case 7: layernorm_kernel<7><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+        default: layernorm_kernel<8><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+    }
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    return VITTF_OK;
+}
+
+extern "C" int vittf_pool_axis(const void* k_f16, int S, int f0, int f1, int D, int axis, int n_out, void* out_f16,
+                               int accumulate, void* stream) {
+    VITTF_REQUIRE(k_f16 && out_f16, "vittf_pool_axis: null pointer");
+    VITTF_REQUIRE(S > 0 && f0 > 0 && f1 > 0 && D > 0 && n_out > 0 && n_out <= S, "vittf_pool_axis: bad sizes");
+    VITTF_REQUIRE(D % 8 == 0, "vittf_pool_axis: D must be a multiple of 8");
+    VITTF_REQUIRE(axis >= 0 && axis <= 2, "vittf_pool_axis: axis must be 0, 1 or 2");
+    PoolParams q;
+    q.k = static_cast<const __half*>(k_f16);
+    q.out = static_cast<__half*>(out_f16);
+    q.S = S; q.T = f0 * f1; q.D = D; q.n_out = n_out; q.f1 = f1; q.accumulate = accumulate;
+    // output (D, A, B, C) contiguous; which of A,B,C are i0 / i1 / o depends on the slicing axis
+    int64_t A, B, C;
+    if (axis == 2) { A = f0; B = f1; C = n_out; q.s0 = B * C; q.s1 = C; q.so = 1; }          // (D, fX, fY, o)
+    else if (axis == 1) { A = f0; B = n_out; C = f1; q.s0 = B * C; q.so = C; q.s1 = 1; }     // (D, fX, o, fZ)
+    else { A = n_out; B = f0; C = f1; q.so = B * C; q.s0 = C; q.s1 = 1; }                    // (D, o, fY, fZ)
+    q.sd = A * B * C;
+    dim3 grid(ceil_div(q.T, 32), ceil_div(D, 64), n_out);
+    pool_axis_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    return VITTF_OK;
+}

@@ -1,0 +1,175 @@
+"""Tensor-level wrappers around the C ABI (one function per exported kernel entry point).
+
+PyTorch is used for device memory and streams only; every computation below happens in
+libvittf_b200.so.  All functions raise ``VittfError`` on failure -- no fallbacks.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import DTYPE_CODE, check, load, ptr, require_cuda, stream_ptr
+
+AXIS_INDEX = {"x": 0, "y": 1, "z": 2}
+
+
+def tok_pad_of(tokens):
+    return (tokens + 127) // 128 * 128
+
+
+def device_arch():
+    out = C.c_int(0)
+    check(load().vittf_device_arch(C.byref(out)), "vittf_device_arch")
+    return out.value
+
+
+def minmax(vol):
+    require_cuda(vol)
+    out = torch.empty(2, dtype=torch.float32, device=vol.device)
+    check(load().vittf_minmax(ptr(vol), vol.numel(), DTYPE_CODE[vol.dtype], ptr(out), stream_ptr(vol.device)), "vittf_minmax")
+    return out
+
+
+def gemm_bf16(a, w, bias, epi, out=None, out2=None, tokens=0, tok_pad=0):
+    """a (M,K) bf16, w (N,K) bf16, bias (N) fp32; see include/vittf.h for the epilogues."""
+    require_cuda(a, w, bias, out, out2)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        if epi in (_lib.EPI_BIAS_BF16, _lib.EPI_BIAS_GELU_BF16):
+            out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+        elif epi == _lib.EPI_QKV_SPLIT:
+            d = N // 3
+            out = torch.empty(M, 2 * d, dtype=torch.bfloat16, device=a.device)
+            out2 = torch.zeros((M // tokens) * d, tok_pad, dtype=torch.bfloat16, device=a.device)
+        elif epi == _lib.EPI_KFEAT_F16:
+            out = torch.empty((M // tokens) * (tokens - 1), N, dtype=torch.float16, device=a.device)
+        else:
+            raise _lib.VittfError("residual epilogue needs the fp32 stream passed as out=")
+    check(load().vittf_gemm_bf16(ptr(a), ptr(w), ptr(bias), ptr(out), ptr(out2), M, N, K, epi, tokens, tok_pad,
+                                 stream_ptr(a.device)), "vittf_gemm_bf16")
+    return (out, out2) if epi == _lib.EPI_QKV_SPLIT else out
+
+
+def attention(qk, vt, batch, tokens, heads, tok_pad):
+    require_cuda(qk, vt)
+    out = torch.empty(batch * tokens, heads * 64, dtype=torch.bfloat16, device=qk.device)
+    check(load().vittf_attention(ptr(qk), ptr(vt), ptr(out), batch, tokens, tok_pad, heads, stream_ptr(qk.device)),
+          "vittf_attention")
+    return out
+
+
+def layernorm(x, w, b):
+    require_cuda(x, w, b)
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    rows = x.numel() // x.shape[-1]
+    check(load().vittf_layernorm(ptr(x), ptr(w), ptr(b), ptr(y), rows, x.shape[-1], stream_ptr(x.device)), "vittf_layernorm")
+    return y
+
+
+def patch_embed(vol, axis, s0, s1, im0, im1, patch, mm, patch_w, patch_b, pos):
+    require_cuda(vol, mm, patch_w, patch_b, pos)
+    D = patch_b.numel()
+    tokens = 1 + (im0 // patch) * (im1 // patch)
+    out = torch.empty(s1 - s0, tokens, D, dtype=torch.float32, device=vol.device)
+    X, Y, Z = vol.shape
+    check(load().vittf_patch_embed(ptr(vol), DTYPE_CODE[vol.dtype], X, Y, Z, AXIS_INDEX[axis], s0, s1, im0, im1, patch, D,
+                                   ptr(mm), ptr(patch_w), ptr(patch_b), ptr(pos), ptr(out), stream_ptr(vol.device)),
+          "vittf_patch_embed")
+    return out
+
+
+def pool_axis(k, f0, f1, axis, n_out, out=None, accumulate=False):
+    """k (S, f0*f1, D) fp16 -> (D, ., ., .) fp16 in the reference layout (infer.py:203)."""
+    require_cuda(k, out)
+    S, T, D = k.shape
+    assert T == f0 * f1
+    shape = {"z": (D, f0, f1, n_out), "y": (D, f0, n_out, f1), "x": (D, n_out, f0, f1)}[axis]
+    if out is None:
+        assert not accumulate
+        out = torch.empty(shape, dtype=torch.float16, device=k.device)
+    assert tuple(out.shape) == shape and out.dtype == torch.float16
+    check(load().vittf_pool_axis(ptr(k), S, f0, f1, D, AXIS_INDEX[axis], n_out, ptr(out), int(accumulate),
+                                 stream_ptr(k.device)), "vittf_pool_axis")
+    return out
+
+
+def sample_prototypes(feats, rel, mode):
+    require_cuda(feats, rel)
+    F, w, h, d = feats.shape
+    A = rel.shape[0]
+    out = torch.empty(A, F, dtype=torch.float32, device=feats.device)
+    check(load().vittf_sample_prototypes(ptr(feats), DTYPE_CODE[feats.dtype], F, w, h, d, ptr(rel), A,
+                                         {"nearest": 0, "bilinear": 1}[mode], ptr(out), stream_ptr(feats.device)),
+          "vittf_sample_prototypes")
+    return out
+
+
+def sim_lowres(feats, protos, want_gram=True):
+    require_cuda(feats, protos)
+    F, w, h, d = feats.shape
+    A = protos.shape[0]
+    n = w * h * d
+    dots = torch.empty(A, n, dtype=torch.float32, device=feats.device)
+    gram = torch.empty(14, n, dtype=torch.float32, device=feats.device) if want_gram else None
+    check(load().vittf_sim_lowres(ptr(feats), DTYPE_CODE[feats.dtype], F, w, h, d, ptr(protos), A, ptr(dots), ptr(gram),
+                                  stream_ptr(feats.device)), "vittf_sim_lowres")
+    return dots, gram
+
+
+def sim_upsample(dots, gram, lr_shape, class_offsets, out_shape, mode, threshold=0.25, exponent=2.0, z0=0, z1=None, out=None):
+    require_cuda(dots, gram, class_offsets, out)
+    w, h, d = lr_shape
+    W, H, D = out_shape
+    z1 = D if z1 is None else z1
+    C_ = class_offsets.numel() - 1
+    if out is None:
+        out = torch.empty(C_, W, H, z1 - z0, dtype=torch.float32, device=dots.device)
+    check(load().vittf_sim_upsample(ptr(dots), ptr(gram), w, h, d, dots.shape[0], ptr(class_offsets), C_, W, H, D, z0, z1,
+                                    mode, float(threshold), float(exponent), ptr(out), stream_ptr(dots.device)),
+          "vittf_sim_upsample")
+    return out
+
+
+def class_max(sims):
+    require_cuda(sims)
+    C_ = sims.shape[0]
+    out = torch.empty(C_, dtype=torch.float32, device=sims.device)
+    check(load().vittf_class_max(ptr(sims), C_, sims[0].numel(), ptr(out), stream_ptr(sims.device)), "vittf_class_max")
+    return out
+
+
+def labels(sims, thresholds_u8=None, mode=0):
+    require_cuda(sims, thresholds_u8)
+    C_ = sims.shape[0]
+    out = torch.empty(sims.shape[1:], dtype=torch.uint8, device=sims.device)
+    check(load().vittf_labels(ptr(sims), DTYPE_CODE[sims.dtype], C_, out.numel(), ptr(thresholds_u8), mode, ptr(out),
+                              stream_ptr(sims.device)), "vittf_labels")
+    return out
+
+
+def sobel_confidence(r_u8):
+    require_cuda(r_u8)
+    W, H, D = r_u8.shape
+    out = torch.empty(W, H, D, dtype=torch.float32, device=r_u8.device)
+    scratch = torch.empty(1, dtype=torch.float32, device=r_u8.device)
+    check(load().vittf_sobel_confidence(ptr(r_u8), W, H, D, ptr(out), ptr(scratch), stream_ptr(r_u8.device)),
+          "vittf_sobel_confidence")
+    return out
+
+
+def bls_solve(t, r_u8, conf, luma_lut, sigma_spatial, lam, diag_min, cg_tol, cg_maxiter, luma_bins):
+    """t (nrhs,W,H,D) fp32, r_u8 (W,H,D) uint8, conf (W,H,D) fp32 or None -> (out fp32 (nrhs,W,H,D), iters int32)."""
+    require_cuda(t, r_u8, conf, luma_lut)
+    nrhs, W, H, D = t.shape
+    prm = _lib.BlsParams(W, H, D, float(sigma_spatial), float(lam), float(diag_min), float(cg_tol), int(cg_maxiter),
+                         int(luma_bins))
+    need = load().vittf_bls_workspace_bytes(C.byref(prm), nrhs)
+    if need < 0:
+        raise _lib.VittfError("vittf_bls_workspace_bytes: bad parameters")
+    ws = torch.empty(need, dtype=torch.uint8, device=t.device)
+    out = torch.empty_like(t)
+    iters = torch.zeros(nrhs, dtype=torch.int32, device=t.device)
+    check(load().vittf_bls_solve(C.byref(prm), ptr(t), ptr(r_u8), ptr(conf), ptr(luma_lut), nrhs, ptr(out), ptr(iters),
+                                 ptr(ws), need, stream_ptr(t.device)), "vittf_bls_solve")
+    return out, iters

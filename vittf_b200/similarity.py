@@ -1,0 +1,41 @@
+"""Prototype-similarity stage on the device (SURVEY.md §0.2 modes NS / REF-NTF / LEGACY).
+
+Two native passes (include/vittf.h): ``vittf_sim_lowres`` reads the feature volume once and produces
+per-voxel prototype dots (+ the 14 Gram scalars that give |interp(f)|^2), ``vittf_sim_upsample``
+evaluates every output voxel from them.  The up-sampled feature volume is never materialised.
+"""
+import torch
+
+from . import _lib, ops
+
+MODES = {"ns": _lib.SIM_NS, "refntf": _lib.SIM_REFNTF, "legacy": _lib.SIM_LEGACY}
+
+
+def class_offsets(annotations, device):
+    sizes = [int(v.shape[0]) for v in annotations.values()]
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + s)
+    return torch.tensor(off, dtype=torch.int32, device=device)
+
+
+def rel_coords(abs_coords, vol_shape, device):
+    """predict_ntf.py:56: voxel index in volume space -> [-1, 1] (X,Y,Z order)."""
+    ext = torch.tensor([list(vol_shape[-3:])], dtype=torch.float32, device=device)
+    return ((abs_coords.to(device).float() + 0.5) / ext * 2.0 - 1.0).contiguous()
+
+
+def similarity_maps(feats, protos, offsets, out_shape=None, mode="ns", exponent=2.0, threshold=0.25, z_range=None,
+                    lowres=None):
+    """feats (F,w,h,d) fp16|fp32 CUDA; protos (A,F) fp32 CUDA (already normalised for ns/legacy);
+    offsets int32 (C+1) CUDA -> fp32 (C, W, H, z1-z0).  `lowres` lets a caller reuse pass 1."""
+    lr = tuple(feats.shape[1:])
+    out_shape = lr if out_shape is None else tuple(out_shape)
+    m = MODES[mode]
+    if m != _lib.SIM_NS and out_shape != lr:
+        raise ValueError("refntf/legacy similarities are defined at feature resolution")
+    if lowres is None:
+        lowres = ops.sim_lowres(feats, protos, want_gram=(m != _lib.SIM_REFNTF))
+    dots, gram = lowres
+    z0, z1 = (0, out_shape[2]) if z_range is None else z_range
+    return ops.sim_upsample(dots, gram, lr, offsets, out_shape, m, threshold, exponent, z0, z1)

@@ -1,0 +1,147 @@
+"""Host side of the ViT K-feature engine.
+
+Reads the parameters of any module that has the DINO attribute layout the reference relies on
+(``model.blocks[-1].attn.qkv`` / ``.attn.num_heads``, /root/reference/infer.py:135,180), pre-processes
+them once (bf16 copies, patch-embed folding, pos-embed interpolation) and drives the native engine
+(vittf_vit_k_features).  ``model.forward`` is never called.
+"""
+import ctypes as C
+import math
+import weakref
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import BlockWeights, VitConfig, check, load, ptr, stream_ptr
+from .ops import AXIS_INDEX
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # infer.py:39
+IMAGENET_STD = (0.229, 0.224, 0.225)   # infer.py:40
+
+
+def fold_patch_embed(weight, bias):
+    """Conv2d(3, D, p, p) applied to three identical grey channels normalised with the ImageNet
+    mean/std == one-channel conv with W' = sum_c W_c/std_c and b' = b - sum W_c mean_c/std_c
+    (SURVEY.md App. D2).  Returns (tap-major (p*p, D) fp32, (D) fp32)."""
+    w = weight.detach().double().cpu()
+    mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float64).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=torch.float64).view(1, 3, 1, 1)
+    w1 = (w / std).sum(dim=1)                                   # (D, p, p)
+    b1 = bias.detach().double().cpu() - (w * mean / std).sum(dim=(1, 2, 3))
+    d = w1.shape[0]
+    return w1.reshape(d, -1).t().contiguous().float(), b1.float()
+
+
+def interpolate_pos_embed(pos_embed, cls_token, patch, im0, im1):
+    """hub `interpolate_pos_encoding` + the cls-token add of `prepare_tokens`, evaluated once per
+    image size on the host.  Returns fp32 (1 + f0*f1, D), row 0 = cls_token + pos[0]."""
+    pos = pos_embed.detach().float().cpu()
+    n = pos.shape[1] - 1
+    f0, f1 = im0 // patch, im1 // patch
+    dim = pos.shape[-1]
+    if f0 * f1 == n and im0 == im1:
+        patch_pos = pos[0, 1:]
+    else:
+        g = int(math.sqrt(n))
+        w0, h0 = f0 + 0.1, f1 + 0.1
+        pp = F.interpolate(pos[:, 1:].reshape(1, g, g, dim).permute(0, 3, 1, 2), scale_factor=(w0 / g, h0 / g),
+                           mode="bicubic")
+        assert int(w0) == pp.shape[-2] and int(h0) == pp.shape[-1]
+        patch_pos = pp.permute(0, 2, 3, 1).reshape(-1, dim)
+    row0 = cls_token.detach().float().cpu().view(1, dim) + pos[0, :1]
+    return torch.cat([row0, patch_pos], dim=0).contiguous()
+
+
+class VitEngine:
+    """Native engine bound to one module's parameters on one CUDA device."""
+
+    def __init__(self, model, device, max_batch=8, max_tokens=4097 + 128):
+        self.device = torch.device(device)
+        blocks = model._modules["blocks"]
+        attn = blocks[-1]._modules["attn"]
+        self.num_heads = attn.num_heads
+        self.embed_dim = attn._modules["qkv"].in_features
+        proj = model.patch_embed.proj
+        self.patch = proj.kernel_size[0]
+        self.depth = len(blocks)
+        self.mlp_hidden = blocks[0].mlp.fc1.out_features
+        self.max_batch = max_batch
+        self.max_tokens = max_tokens
+        dev = self.device
+        self._keep = []      # device tensors referenced by raw pointers inside the engine
+
+        def f32(t):
+            t = t.detach().to(dev, torch.float32).contiguous()
+            self._keep.append(t)
+            return t
+
+        def bf16(t):
+            t = t.detach().to(dev, torch.bfloat16).contiguous()
+            self._keep.append(t)
+            return t
+
+        pw, pb = fold_patch_embed(proj.weight, proj.bias)
+        self.patch_w, self.patch_b = f32(pw), f32(pb)
+        arr = (BlockWeights * self.depth)()
+        for i, blk in enumerate(blocks):
+            fields = dict(ln1_w=f32(blk.norm1.weight), ln1_b=f32(blk.norm1.bias),
+                          qkv_w=bf16(blk.attn.qkv.weight), qkv_b=f32(blk.attn.qkv.bias),
+                          proj_w=bf16(blk.attn.proj.weight), proj_b=f32(blk.attn.proj.bias),
+                          ln2_w=f32(blk.norm2.weight), ln2_b=f32(blk.norm2.bias),
+                          fc1_w=bf16(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias),
+                          fc2_w=bf16(blk.mlp.fc2.weight), fc2_b=f32(blk.mlp.fc2.bias))
+            for k, v in fields.items():
+                setattr(arr[i], k, v.data_ptr())
+        self._blocks = arr
+        self._pos_src = (model.pos_embed.detach().cpu().clone(), model.cls_token.detach().cpu().clone())
+        self._pos_cache = {}
+        cfg = VitConfig(self.embed_dim, self.depth, self.num_heads, self.patch, self.mlp_hidden)
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(load().vittf_vit_create(C.byref(handle), C.byref(cfg), arr, ptr(self.patch_w), ptr(self.patch_b),
+                                          max_batch, max_tokens), "vittf_vit_create")
+        self._handle = handle
+        self._ws = None
+        self._finalizer = weakref.finalize(self, load().vittf_vit_destroy, handle)
+
+    def pos_for(self, im0, im1):
+        key = (im0, im1)
+        if key not in self._pos_cache:
+            self._pos_cache[key] = interpolate_pos_embed(self._pos_src[0], self._pos_src[1], self.patch, im0, im1).to(self.device)
+        return self._pos_cache[key]
+
+    def _workspace(self, batch, tokens):
+        need = load().vittf_vit_workspace_bytes(self._handle, batch, tokens)
+        if need < 0:
+            raise _lib.VittfError("vittf_vit_workspace_bytes: bad arguments")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def k_features(self, vol, axis, s0, s1, im0, im1, mm, out=None):
+        """K features of the patch tokens of slices [s0, s1): fp16 (s1-s0, f0*f1, D)."""
+        _lib.require_cuda(vol, mm, out)
+        f0, f1 = im0 // self.patch, im1 // self.patch
+        tokens = 1 + f0 * f1
+        B = s1 - s0
+        if out is None:
+            out = torch.empty(B, f0 * f1, self.embed_dim, dtype=torch.float16, device=self.device)
+        ws = self._workspace(B, tokens)
+        X, Y, Z = vol.shape
+        check(load().vittf_vit_k_features(self._handle, ptr(vol), _lib.DTYPE_CODE[vol.dtype], X, Y, Z, AXIS_INDEX[axis],
+                                          s0, s1, im0, im1, ptr(mm), ptr(self.pos_for(im0, im1)), ptr(out), ptr(ws),
+                                          ws.numel(), stream_ptr(self.device)), "vittf_vit_k_features")
+        return out
+
+
+_ENGINES = weakref.WeakKeyDictionary()
+
+
+def engine_for(model, device, max_batch=8, max_tokens=4097 + 128):
+    """One engine per (module, device); parameters are read once (cache keyed on the module)."""
+    per_model = _ENGINES.setdefault(model, {})
+    key = (str(device), max_batch, max_tokens)
+    if key not in per_model:
+        per_model[key] = VitEngine(model, device, max_batch, max_tokens)
+    return per_model[key]
