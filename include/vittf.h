@@ -39,6 +39,10 @@ const char* vittf_last_error(void);
 int vittf_version(void);
 /* compute capability of the current device, major*10+minor (100 on B200) */
 int vittf_device_arch(int* out_arch);
+/* number of kernels this library has launched in this process since the last reset
+ * (bench.py reports it as `gpu_launches`) */
+int64_t vittf_launch_count(void);
+void vittf_launch_count_reset(void);
 
 /* =====================================================================================
  * Stage 1 -- ViT K-feature extraction (infer.py:130-210 compute_qkv, :314-340 main loop)
@@ -93,12 +97,24 @@ int vittf_vit_k_features(vittf_vit* v, const void* vol, int vol_dtype, int X, in
                          int im0, int im1, const float* minmax2, const float* pos_embed, void* out_k_f16,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Optional device-side timing of the kernels launched inside vittf_vit_k_features: cudaEvent pairs
+ * on the caller's stream around every attention (kind 0) and GEMM (kind 1) launch.  bench.py uses
+ * it for the roofline of the dominant kernel.  _read synchronises, returns and clears the totals. */
+int vittf_vit_timing_enable(vittf_vit* v, int enable);
+int vittf_vit_timing_read(vittf_vit* v, double* ms_by_kind2, int64_t* launches_by_kind2);
+
 /* AdaptiveAvgPool3d along the slice axis only + permute to the reference's (D,fX,fY,fZ)
  * layout (infer.py:203 with pool_fn from :329): k (S, f0*f1, D) fp16 -> out fp16.
  * n_out == S reproduces the `_noop` pool of single-axis runs (infer.py:326).
- * accumulate != 0 adds (in fp16, rounding like infer.py:332) into `out` instead of storing. */
-int vittf_pool_axis(const void* k_f16, int S, int f0, int f1, int D, int axis, int n_out, void* out_f16,
-                    int accumulate, void* stream);
+ * accumulate != 0 adds (in fp16, rounding like infer.py:332) into `out` instead of storing.
+ * Sharding: S is the GLOBAL slice count, k holds slices [slice0, slice0+n_local)
+ * and only the output slabs [o0, o1) are produced (their windows must lie inside k's range). */
+int vittf_pool_axis(const void* k_f16, int S, int slice0, int n_local, int f0, int f1, int D, int axis, int n_out,
+                    int o0, int o1, void* out_f16, int accumulate, void* stream);
+
+/* out = fp16(out + in): the running sum over the three slicing axes (infer.py:332), used when
+ * the per-axis volumes come from different GPUs. */
+int vittf_accumulate_f16(void* out_f16, const void* in_f16, int64_t n, void* stream);
 
 /* -------- individually exported building blocks (unit-tested against torch) ---------- */
 enum { VITTF_EPI_BIAS_BF16 = 0, VITTF_EPI_BIAS_GELU_BF16 = 1, VITTF_EPI_BIAS_RESID_F32 = 2,

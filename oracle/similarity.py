@@ -92,24 +92,25 @@ def legacy(feats, annotations, volume_shape, exponent=2.0):
 
 
 @torch.no_grad()
-def ns_composite(feats, protos, class_offsets, out_shape, exponent=2.0, slab=16):
+def ns_composite(feats, protos, class_offsets, out_shape, exponent=2.0, slab=16, z_range=None):
     """North-star order: up-sample FEATURES -> normalise -> dot -> clamp/pow -> class max.
 
     feats (F,w,h,d) any float dtype; protos (A,F) fp32 (normalised here, as the
     legacy path normalises its prototypes); class_offsets list of C+1 ints.
     Evaluated in z-slabs of the OUTPUT so the up-sampled features never exceed
-    host memory.  Returns fp32 (C, *out_shape)."""
+    host memory.  Returns fp32 (C, W, H, z1-z0) for the output z-range (default: all of D)."""
     f32 = feats.float()
     pn = F.normalize(protos.float(), dim=-1)
     n_cls = len(class_offsets) - 1
-    out = torch.empty((n_cls,) + tuple(out_shape), dtype=torch.float32)
     W, H, D = out_shape
+    zlo, zhi = (0, D) if z_range is None else z_range
+    out = torch.empty((n_cls, W, H, zhi - zlo), dtype=torch.float32)
     w, h, d = f32.shape[1:]
     # F.interpolate over a z-slab must reproduce the full-volume index rule, so the slab
     # is cut on the OUTPUT grid and the source window is chosen to contain every tap.
     scale = d / D
-    for z0 in range(0, D, slab):
-        z1 = min(D, z0 + slab)
+    for z0 in range(zlo, zhi, slab):
+        z1 = min(zhi, z0 + slab)
         src = [max((z + 0.5) * scale - 0.5, 0.0) for z in range(z0, z1)]
         lo = int(src[0])
         hi = min(int(src[-1]) + 1, d - 1)
@@ -117,7 +118,7 @@ def ns_composite(feats, protos, class_offsets, out_shape, exponent=2.0, slab=16)
         up = F.normalize(up, dim=0)
         s = torch.einsum("fwhd,af->awhd", up, pn).clamp(0, 1) ** exponent
         for c in range(n_cls):
-            out[c, :, :, z0:z1] = s[class_offsets[c]:class_offsets[c + 1]].max(dim=0).values
+            out[c, :, :, z0 - zlo:z1 - zlo] = s[class_offsets[c]:class_offsets[c + 1]].max(dim=0).values
     return out
 
 

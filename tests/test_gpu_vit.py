@@ -29,7 +29,7 @@ def test_layernorm(D):
     x = torch.randn(1001, D, device="cuda") * 3 + 1
     w, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
     ref = F.layer_norm(x, (D,), w, b, eps=1e-6)
-    assert (ops.layernorm(x, w, b).float() - ref).abs().max().item() < 3e-2
+    assert ((ops.layernorm(x, w, b).float() - ref).abs() / (1.0 + ref.abs())).max().item() < 8e-3   # bf16 output
 
 
 @pytest.mark.parametrize("axis", ["z", "y", "x"])

@@ -43,12 +43,17 @@ _SIGNATURES = {
     "vittf_last_error": (C.c_char_p, []),
     "vittf_version": (_i, []),
     "vittf_device_arch": (_i, [C.POINTER(_i)]),
+    "vittf_launch_count": (_i64, []),
+    "vittf_launch_count_reset": (None, []),
+    "vittf_vit_timing_enable": (_i, [_p, _i]),
+    "vittf_vit_timing_read": (_i, [_p, C.POINTER(_d), C.POINTER(_i64)]),
     "vittf_minmax": (_i, [_p, _i64, _i, _p, _p]),
     "vittf_vit_create": (_i, [C.POINTER(_p), C.POINTER(VitConfig), C.POINTER(BlockWeights), _p, _p, _i, _i]),
     "vittf_vit_destroy": (None, [_p]),
     "vittf_vit_workspace_bytes": (_i64, [_p, _i, _i]),
     "vittf_vit_k_features": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _p]),
-    "vittf_pool_axis": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "vittf_pool_axis": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "vittf_accumulate_f16": (_i, [_p, _p, _i64, _p]),
     "vittf_gemm_bf16": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vittf_attention": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "vittf_layernorm": (_i, [_p, _p, _p, _p, _i64, _i, _p]),

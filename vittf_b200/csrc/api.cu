@@ -4,7 +4,14 @@
 
 #include "common.cuh"
 
+#include <atomic>
+
 static thread_local char g_last_error[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void vittf_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t vittf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void vittf_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
 
 void vittf_set_error(const char* fmt, ...) {
     va_list ap;

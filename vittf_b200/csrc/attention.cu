@@ -274,5 +274,6 @@ extern "C" int vittf_attention(const void* qk, const void* vt, void* out, int B,
     dim3 grid(ceil_div(tokens, 2 * BQ), heads, B);
     attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tm_qk, tm_vt, p);
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }

@@ -319,6 +319,7 @@ extern "C" int vittf_sobel_confidence(const uint8_t* r_u8, int W, int H, int D, 
     sobel_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(r_u8, W, H, D, out, scratch_max);
     confidence_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(out, n, scratch_max);
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(2);
     return VITTF_OK;
 }
 
@@ -390,5 +391,6 @@ extern "C" int vittf_bls_solve(const vittf_bls_params* p, const float* t, const 
     slice_kernel<<<gp, 256, 0, s>>>(g, r_u8, luma_lut, y, nrhs, out);
     if (iters_out) copy_iters_kernel<<<1, 64, 0, s>>>(sc, nrhs, iters_out);
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(2 + 10 + 1 + 2 + 4 * p->cg_maxiter + 1 + (iters_out ? 1 : 0));
     return VITTF_OK;
 }

@@ -42,6 +42,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 int vittf_num_sms();
+void vittf_count_launches(int n);
 
 // 2-D .. 4-D tiled tensor maps (bf16/fp16 elements), built through the driver entry point so
 // the library has no link-time dependency on libcuda.

@@ -239,6 +239,7 @@ int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t 
     const int grid = tiles < vittf_num_sms() ? tiles : vittf_num_sms();
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }
 

@@ -309,14 +309,17 @@ int launch_lowres(const T* feats, int F, int w, int h, int d, const float* proto
             if (first && GRAM) sim_lowres_kernel<T, 32, true><<<grid, 128, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
             else sim_lowres_kernel<T, 32, false><<<grid, 128, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
             a_base += 32;
+            vittf_count_launches(1);
         } else if (rem > 8) {
             if (first && GRAM) sim_lowres_kernel<T, 16, true><<<grid, 128, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
             else sim_lowres_kernel<T, 16, false><<<grid, 128, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
             a_base += 16;
+            vittf_count_launches(1);
         } else {
             if (first && GRAM) sim_lowres_kernel<T, 8, true><<<grid, 128, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
             else sim_lowres_kernel<T, 8, false><<<grid, 128, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
             a_base += 8;
+            vittf_count_launches(1);
         }
         first = false;
     }
@@ -339,6 +342,7 @@ extern "C" int vittf_sample_prototypes(const void* feats, int feat_dtype, int F,
     else
         VITTF_REQUIRE(false, "vittf_sample_prototypes: features must be fp16 or fp32");
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }
 
@@ -376,6 +380,7 @@ extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, i
     if (blocks > cap) blocks = cap;
     sim_upsample_kernel<<<static_cast<unsigned>(blocks), 256, (C + 1) * sizeof(int), static_cast<cudaStream_t>(stream)>>>(q);
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }
 
@@ -386,6 +391,7 @@ extern "C" int vittf_class_max(const float* sims, int C, int64_t n, float* out, 
     dim3 grid(vittf_num_sms() * 2, C);
     class_max_kernel<<<grid, 256, 0, s>>>(sims, n, out);
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(2);
     return VITTF_OK;
 }
 
@@ -404,5 +410,6 @@ extern "C" int vittf_labels(const void* sims, int sims_dtype, int C, int64_t n, 
     else
         VITTF_REQUIRE(false, "vittf_labels: similarity maps must be uint8 or fp32");
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }

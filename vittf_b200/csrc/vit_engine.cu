@@ -4,6 +4,8 @@
 // block's qkv projection for the patch tokens.  The full 3D-wide qkv tensor the
 // reference copies to the host per batch (infer.py:134) never exists.
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -13,6 +15,10 @@ struct vittf_vit {
     const float* patch_w;
     const float* patch_b;
     int max_batch, max_tokens;
+    // optional per-kernel timing (bench.py roofline): event pairs around attention (0) / GEMM (1) launches
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[2];
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
 };
 
 namespace {
@@ -46,7 +52,49 @@ Workspace carve(const vittf_vit_config& c, int batch, int tokens, uint8_t* base)
     w.total = off;
     return w;
 }
+
+struct ScopedTimer {
+    vittf_vit* v;
+    int kind;
+    cudaStream_t s;
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    ScopedTimer(vittf_vit* v_, int kind_, cudaStream_t s_) : v(v_), kind(kind_), s(s_) {
+        if (!v->timing) return;
+        if (!v->pool.empty()) { ev = v->pool.back(); v->pool.pop_back(); }
+        else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+        cudaEventRecord(ev.first, s);
+    }
+    ~ScopedTimer() {
+        if (!ev.first) return;
+        cudaEventRecord(ev.second, s);
+        v->pending[kind].push_back(ev);
+    }
+};
 }  // namespace
+
+extern "C" int vittf_vit_timing_enable(vittf_vit* v, int enable) {
+    VITTF_REQUIRE(v, "vittf_vit_timing_enable: null engine");
+    v->timing = enable != 0;
+    return VITTF_OK;
+}
+
+extern "C" int vittf_vit_timing_read(vittf_vit* v, double* ms_by_kind2, int64_t* launches_by_kind2) {
+    VITTF_REQUIRE(v && ms_by_kind2 && launches_by_kind2, "vittf_vit_timing_read: null pointer");
+    for (int k = 0; k < 2; ++k) {
+        double total = 0.0;
+        for (auto& e : v->pending[k]) {
+            VITTF_CHECK_CUDA(cudaEventSynchronize(e.second));
+            float ms = 0.0f;
+            VITTF_CHECK_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+            total += ms;
+            v->pool.push_back(e);
+        }
+        ms_by_kind2[k] = total;
+        launches_by_kind2[k] = static_cast<int64_t>(v->pending[k].size());
+        v->pending[k].clear();
+    }
+    return VITTF_OK;
+}
 
 extern "C" int vittf_vit_create(vittf_vit** out, const vittf_vit_config* cfg, const vittf_block_weights* blocks_host,
                                 const float* patch_w, const float* patch_b, int max_batch, int max_tokens) {
@@ -72,6 +120,9 @@ extern "C" int vittf_vit_create(vittf_vit** out, const vittf_vit_config* cfg, co
 
 extern "C" void vittf_vit_destroy(vittf_vit* v) {
     if (!v) return;
+    for (int k = 0; k < 2; ++k)
+        for (auto& e : v->pending[k]) v->pool.push_back(e);
+    for (auto& e : v->pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete[] v->blocks;
     delete v;
 }
@@ -107,12 +158,17 @@ extern "C" int vittf_vit_k_features(vittf_vit* v, const void* vol, int vol_dtype
     for (int l = 0; l + 1 < c.depth; ++l) {
         const vittf_block_weights& bw = v->blocks[l];
         VITTF_CHECK(vittf_layernorm(w.x, bw.ln1_w, bw.ln1_b, w.xn, M, D, stream));
-        VITTF_CHECK(vittf_gemm_bf16(w.xn, bw.qkv_w, bw.qkv_b, w.qk, w.vt, M, 3 * D, D, VITTF_EPI_QKV_SPLIT, tokens, tok_pad, stream));
-        VITTF_CHECK(vittf_attention(w.qk, w.vt, w.att, B, tokens, tok_pad, c.num_heads, stream));
-        VITTF_CHECK(vittf_gemm_bf16(w.att, bw.proj_w, bw.proj_b, w.x, nullptr, M, D, D, VITTF_EPI_BIAS_RESID_F32, tokens, tok_pad, stream));
+        { ScopedTimer t(v, 1, s);
+          VITTF_CHECK(vittf_gemm_bf16(w.xn, bw.qkv_w, bw.qkv_b, w.qk, w.vt, M, 3 * D, D, VITTF_EPI_QKV_SPLIT, tokens, tok_pad, stream)); }
+        { ScopedTimer t(v, 0, s);
+          VITTF_CHECK(vittf_attention(w.qk, w.vt, w.att, B, tokens, tok_pad, c.num_heads, stream)); }
+        { ScopedTimer t(v, 1, s);
+          VITTF_CHECK(vittf_gemm_bf16(w.att, bw.proj_w, bw.proj_b, w.x, nullptr, M, D, D, VITTF_EPI_BIAS_RESID_F32, tokens, tok_pad, stream)); }
         VITTF_CHECK(vittf_layernorm(w.x, bw.ln2_w, bw.ln2_b, w.xn, M, D, stream));
-        VITTF_CHECK(vittf_gemm_bf16(w.xn, bw.fc1_w, bw.fc1_b, w.hid, nullptr, M, c.mlp_hidden, D, VITTF_EPI_BIAS_GELU_BF16, tokens, tok_pad, stream));
-        VITTF_CHECK(vittf_gemm_bf16(w.hid, bw.fc2_w, bw.fc2_b, w.x, nullptr, M, D, c.mlp_hidden, VITTF_EPI_BIAS_RESID_F32, tokens, tok_pad, stream));
+        { ScopedTimer t(v, 1, s);
+          VITTF_CHECK(vittf_gemm_bf16(w.xn, bw.fc1_w, bw.fc1_b, w.hid, nullptr, M, c.mlp_hidden, D, VITTF_EPI_BIAS_GELU_BF16, tokens, tok_pad, stream)); }
+        { ScopedTimer t(v, 1, s);
+          VITTF_CHECK(vittf_gemm_bf16(w.hid, bw.fc2_w, bw.fc2_b, w.x, nullptr, M, D, c.mlp_hidden, VITTF_EPI_BIAS_RESID_F32, tokens, tok_pad, stream)); }
     }
     // last block: norm1 + K rows [D, 2D) of attn.qkv only
     const vittf_block_weights& last = v->blocks[c.depth - 1];

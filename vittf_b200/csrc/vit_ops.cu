@@ -196,6 +196,7 @@ struct PoolParams {
     const __half* k;
     __half* out;
     int S, T, D, n_out;
+    int slice0, n_local, o0;   // k holds global slices [slice0, slice0+n_local); blockIdx.z + o0 = output slab
     int f1;
     int64_t sd, s0, s1, so;  // output strides (elements) of d, i0, i1, o
     int accumulate;
@@ -203,9 +204,10 @@ struct PoolParams {
 
 __global__ void __launch_bounds__(256) pool_axis_kernel(PoolParams q) {
     __shared__ float tile[32][65];
-    const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 64, o = blockIdx.z;
-    const int w0 = static_cast<int>((static_cast<int64_t>(o) * q.S) / q.n_out);
-    const int w1 = static_cast<int>((static_cast<int64_t>(o + 1) * q.S + q.n_out - 1) / q.n_out);
+    const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 64, o = blockIdx.z + q.o0;
+    // AdaptiveAvgPool window [floor(o*S/n), ceil((o+1)*S/n)) in global slice indices, then local
+    const int w0 = static_cast<int>((static_cast<int64_t>(o) * q.S) / q.n_out) - q.slice0;
+    const int w1 = static_cast<int>((static_cast<int64_t>(o + 1) * q.S + q.n_out - 1) / q.n_out) - q.slice0;
     // load: thread -> (token row = tid/8, 8 halves at d = (tid%8)*8)
     {
         const int tr = threadIdx.x >> 3, dc = (threadIdx.x & 7) * 8;
@@ -244,7 +246,41 @@ __global__ void __launch_bounds__(256) pool_axis_kernel(PoolParams q) {
     }
 }
 
+
+// fp16 running sum of per-axis volumes (infer.py:332): out = fp16(out + in), 128-bit vectorised
+__global__ void __launch_bounds__(256) accumulate_f16_kernel(__half* __restrict__ out, const __half* __restrict__ in, int64_t n) {
+    const int64_t nvec = n / 8;
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    const uint4* i4 = reinterpret_cast<const uint4*>(in);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        uint4 a = o4[i];
+        const uint4 b = __ldg(i4 + i);
+        __half2* ah = reinterpret_cast<__half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ah[k] = __hadd2(ah[k], bh[k]);
+        o4[i] = a;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = __hadd(out[i], in[i]);
+}
+
 }  // namespace
+
+extern "C" int vittf_accumulate_f16(void* out_f16, const void* in_f16, int64_t n, void* stream) {
+    VITTF_REQUIRE(out_f16 && in_f16 && n > 0, "vittf_accumulate_f16: bad arguments");
+    VITTF_REQUIRE(((reinterpret_cast<uintptr_t>(out_f16) | reinterpret_cast<uintptr_t>(in_f16)) & 15) == 0,
+                  "vittf_accumulate_f16: buffers must be 16-byte aligned");
+    int64_t blocks = ceil_div_ll(n / 8 + 1, 256);
+    const int64_t cap = static_cast<int64_t>(vittf_num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    accumulate_f16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<__half*>(out_f16), static_cast<const __half*>(in_f16), n);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
 
 extern "C" int vittf_minmax(const void* vol, int64_t n, int dtype, float* out2, void* stream) {
     VITTF_REQUIRE(vol && out2 && n > 0, "vittf_minmax: bad arguments");
@@ -259,6 +295,7 @@ extern "C" int vittf_minmax(const void* vol, int64_t n, int dtype, float* out2, 
         default: VITTF_REQUIRE(false, "vittf_minmax: unsupported dtype %d", dtype);
     }
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(2);
     return VITTF_OK;
 }
 
@@ -297,6 +334,7 @@ extern "C" int vittf_patch_embed(const void* vol, int vol_dtype, int X, int Y, i
     }
 #undef LAUNCH_PE
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }
 
@@ -318,27 +356,38 @@ extern "C" int vittf_layernorm(const float* x, const float* w, const float* b, v
         default: layernorm_kernel<8><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
     }
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }
 
-extern "C" int vittf_pool_axis(const void* k_f16, int S, int f0, int f1, int D, int axis, int n_out, void* out_f16,
-                               int accumulate, void* stream) {
+extern "C" int vittf_pool_axis(const void* k_f16, int S, int slice0, int n_local, int f0, int f1, int D, int axis,
+                               int n_out, int o0, int o1, void* out_f16, int accumulate, void* stream) {
     VITTF_REQUIRE(k_f16 && out_f16, "vittf_pool_axis: null pointer");
     VITTF_REQUIRE(S > 0 && f0 > 0 && f1 > 0 && D > 0 && n_out > 0 && n_out <= S, "vittf_pool_axis: bad sizes");
+    VITTF_REQUIRE(o0 >= 0 && o1 > o0 && o1 <= n_out, "vittf_pool_axis: slab range [%d,%d) outside [0,%d)", o0, o1, n_out);
+    {
+        const int need0 = static_cast<int>((static_cast<int64_t>(o0) * S) / n_out);
+        const int need1 = static_cast<int>((static_cast<int64_t>(o1) * S + n_out - 1) / n_out);
+        VITTF_REQUIRE(slice0 <= need0 && slice0 + n_local >= need1,
+                      "vittf_pool_axis: slabs [%d,%d) need slices [%d,%d) but k holds [%d,%d)", o0, o1, need0, need1, slice0,
+                      slice0 + n_local);
+    }
     VITTF_REQUIRE(D % 8 == 0, "vittf_pool_axis: D must be a multiple of 8");
     VITTF_REQUIRE(axis >= 0 && axis <= 2, "vittf_pool_axis: axis must be 0, 1 or 2");
     PoolParams q;
     q.k = static_cast<const __half*>(k_f16);
     q.out = static_cast<__half*>(out_f16);
     q.S = S; q.T = f0 * f1; q.D = D; q.n_out = n_out; q.f1 = f1; q.accumulate = accumulate;
+    q.slice0 = slice0; q.n_local = n_local; q.o0 = o0;
     // output (D, A, B, C) contiguous; which of A,B,C are i0 / i1 / o depends on the slicing axis
     int64_t A, B, C;
     if (axis == 2) { A = f0; B = f1; C = n_out; q.s0 = B * C; q.s1 = C; q.so = 1; }          // (D, fX, fY, o)
     else if (axis == 1) { A = f0; B = n_out; C = f1; q.s0 = B * C; q.so = C; q.s1 = 1; }     // (D, fX, o, fZ)
     else { A = n_out; B = f0; C = f1; q.so = B * C; q.s0 = C; q.s1 = 1; }                    // (D, o, fY, fZ)
     q.sd = A * B * C;
-    dim3 grid(ceil_div(q.T, 32), ceil_div(D, 64), n_out);
+    dim3 grid(ceil_div(q.T, 32), ceil_div(D, 64), o1 - o0);
     pool_axis_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
     VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }

@@ -106,11 +106,11 @@ def _pool_target(pool_fn, axis, n_slices, f_sz3):
     return None
 
 
-def k_features_axis_device(vol_dev, engine, im_sizes, slice_along, batch_size, n_out, mm=None, slice_range=None,
-                           out=None, accumulate=False):
+def k_features_axis_device(vol_dev, engine, im_sizes, slice_along, batch_size, n_out, mm=None, rank=0, world=1):
     """Device-resident core of compute_qkv: per-axis K features pooled to `n_out` slabs along the slice
-    axis, in the reference layout (D, ., ., .).  `slice_range` restricts the work to slices [a, b)
-    (multi-GPU sharding); the pooled slabs of other ranges are left untouched in `out`."""
+    axis, in the reference layout (D, ., ., .).  With world > 1 this rank evaluates only the slices of
+    its slab range (vittf_b200/dist.py) and the returned buffer is zero elsewhere."""
+    from . import dist
     r, c = AXIS_IMAGE_DIMS[slice_along]
     s_dim = AXIS_SLICE_DIM[slice_along]
     im0, im1 = im_sizes[r], im_sizes[c]
@@ -119,14 +119,19 @@ def k_features_axis_device(vol_dev, engine, im_sizes, slice_along, batch_size, n
     S = vol_dev.shape[s_dim]
     if mm is None:
         mm = ops.minmax(vol_dev)
-    a, b = (0, S) if slice_range is None else slice_range
-    kbuf = torch.empty(b - a, f0 * f1, engine.embed_dim, dtype=torch.float16, device=vol_dev.device)
-    for s0 in range(a, b, batch_size):
-        s1 = min(b, s0 + batch_size)
-        engine.k_features(vol_dev, slice_along, s0, s1, im0, im1, mm, out=kbuf[s0 - a:s1 - a])
-    if slice_range is None:
-        return ops.pool_axis(kbuf, f0, f1, slice_along, n_out, out=out, accumulate=accumulate)
-    return kbuf
+    o0, o1 = dist.slab_range(n_out, world, rank)
+    a, b = dist.slices_for_slabs(S, n_out, o0, o1)
+    shape = {"z": (engine.embed_dim, f0, f1, n_out), "y": (engine.embed_dim, f0, n_out, f1),
+             "x": (engine.embed_dim, n_out, f0, f1)}[slice_along]
+    alloc = torch.empty if world == 1 else torch.zeros
+    out = alloc(shape, dtype=torch.float16, device=vol_dev.device)
+    if b > a:
+        kbuf = torch.empty(b - a, f0 * f1, engine.embed_dim, dtype=torch.float16, device=vol_dev.device)
+        for s0 in range(a, b, batch_size):
+            s1 = min(b, s0 + batch_size)
+            engine.k_features(vol_dev, slice_along, s0, s1, im0, im1, mm, out=kbuf[s0 - a:s1 - a])
+        ops.pool_axis(kbuf, f0, f1, slice_along, n_out, out=out, total_slices=S, slice0=a, slabs=(o0, o1))
+    return out
 
 
 def compute_qkv(vol, model, patch_size, im_sizes, pool_fn=_noop, batch_size=1, slice_along='z', return_keys=['q', 'k', 'v'],
@@ -167,9 +172,13 @@ def _max_tokens(im_sizes, patch):
     return 1 + f[-1] * f[-2]
 
 
-def feature_volume(vol, model, patch_size=8, feature_output_size=64, batch_size=8, dev=None, slice_along='all'):
+def feature_volume(vol, model, patch_size=8, feature_output_size=64, batch_size=8, dev=None, slice_along='all',
+                   rank=0, world=1, group=None):
     """The 3-axis loop of infer.py:327-333 with everything kept on the device: returns the merged fp16
-    feature volume (D, fX, fY, fZ) as a CUDA tensor (z, then y, then x summed in fp16)."""
+    feature volume (D, fX, fY, fZ) as a CUDA tensor (z, then y, then x summed in fp16).  With world > 1
+    the slices of every axis are sharded over the ranks and one all-reduce per axis assembles the
+    (replicated) result."""
+    from . import dist
     dev = _cuda_device(dev)
     v = vol.squeeze().to(dev)
     if v.dtype not in (torch.uint8, torch.float16, torch.float32):
@@ -183,7 +192,10 @@ def feature_volume(vol, model, patch_size=8, feature_output_size=64, batch_size=
     with torch.no_grad():
         for ax in axes:
             n_out = f_sz[AXIS_SLICE_DIM[ax]] if slice_along == 'all' else v.shape[AXIS_SLICE_DIM[ax]]
-            out = k_features_axis_device(v, engine, im_sz, ax, batch_size, n_out, mm=mm, out=out, accumulate=out is not None)
+            part = k_features_axis_device(v, engine, im_sz, ax, batch_size, n_out, mm=mm, rank=rank, world=world)
+            if world > 1:
+                dist.all_reduce_disjoint(part, group)
+            out = part if out is None else ops.accumulate_f16(out, part)
     return out
 
 

@@ -79,18 +79,30 @@ def patch_embed(vol, axis, s0, s1, im0, im1, patch, mm, patch_w, patch_b, pos):
     return out
 
 
-def pool_axis(k, f0, f1, axis, n_out, out=None, accumulate=False):
-    """k (S, f0*f1, D) fp16 -> (D, ., ., .) fp16 in the reference layout (infer.py:203)."""
+def pool_axis(k, f0, f1, axis, n_out, out=None, accumulate=False, total_slices=None, slice0=0, slabs=None):
+    """k (S, f0*f1, D) fp16 -> (D, ., ., .) fp16 in the reference layout (infer.py:203).
+    Sharded use: k holds global slices [slice0, slice0+S) of `total_slices`; only output slabs
+    `slabs=(o0, o1)` are written."""
     require_cuda(k, out)
-    S, T, D = k.shape
+    n_local, T, D = k.shape
+    S = n_local if total_slices is None else total_slices
+    o0, o1 = (0, n_out) if slabs is None else slabs
     assert T == f0 * f1
     shape = {"z": (D, f0, f1, n_out), "y": (D, f0, n_out, f1), "x": (D, n_out, f0, f1)}[axis]
     if out is None:
         assert not accumulate
         out = torch.empty(shape, dtype=torch.float16, device=k.device)
     assert tuple(out.shape) == shape and out.dtype == torch.float16
-    check(load().vittf_pool_axis(ptr(k), S, f0, f1, D, AXIS_INDEX[axis], n_out, ptr(out), int(accumulate),
-                                 stream_ptr(k.device)), "vittf_pool_axis")
+    check(load().vittf_pool_axis(ptr(k), S, slice0, n_local, f0, f1, D, AXIS_INDEX[axis], n_out, o0, o1, ptr(out),
+                                 int(accumulate), stream_ptr(k.device)), "vittf_pool_axis")
+    return out
+
+
+def accumulate_f16(out, inp):
+    """out = fp16(out + inp) in place (infer.py:332)."""
+    require_cuda(out, inp)
+    assert out.dtype == torch.float16 and inp.dtype == torch.float16 and out.shape == inp.shape
+    check(load().vittf_accumulate_f16(ptr(out), ptr(inp), out.numel(), stream_ptr(out.device)), "vittf_accumulate_f16")
     return out
 
 

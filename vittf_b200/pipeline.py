@@ -1,0 +1,34 @@
+"""Whole hot path for one volume: raw voxels -> 3-axis ViT K-feature volume -> prototype similarity
+(north-star order: trilinear up-sampling of the features, L2 normalisation, dot, clamp/pow, per-class
+max) -> label volume.  Used by bench.py, __graft_entry__.smoke() and the end-to-end tests; every
+arithmetic step is a libvittf_b200 kernel.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import dist, infer, ops
+from .similarity import class_offsets, rel_coords, similarity_maps
+
+
+def prototypes(feats, annotations, vol_shape, mode="bilinear", normalize=True):
+    """Prototype vectors of the annotated voxels (infer.py:48-72 lookup), (A, F) fp32 on the device."""
+    pts = torch.cat(list(annotations.values()))
+    rel = rel_coords(pts, vol_shape, feats.device)
+    protos = ops.sample_prototypes(feats, rel, mode)
+    return F.normalize(protos, dim=-1).contiguous() if normalize else protos
+
+
+def volume_to_similarity(vol_dev, model, annotations, patch=8, fos=64, batch_size=8, out_shape=None, exponent=2.0,
+                         rank=0, world=1, group=None, want_labels=True):
+    """Returns (feature volume fp16 (D,f,f,f), similarity maps fp32 (C,W,H,z1-z0), labels uint8 (W,H,z1-z0)
+    or None, (z0, z1)).  With world > 1 the maps/labels cover this rank's z-slab."""
+    feats = infer.feature_volume(vol_dev, model, patch, fos, batch_size, dev=vol_dev.device, rank=rank, world=world,
+                                 group=group)
+    vol_shape = tuple(vol_dev.shape[-3:])
+    out_shape = vol_shape if out_shape is None else tuple(out_shape)
+    protos = prototypes(feats, annotations, vol_shape)
+    offs = class_offsets(annotations, feats.device)
+    zr = dist.z_range(out_shape[2], world, rank)
+    sims = similarity_maps(feats, protos, offs, out_shape, mode="ns", exponent=exponent, z_range=zr)
+    labels = ops.labels(sims, None, mode=1) if want_labels else None
+    return feats, sims, labels, zr

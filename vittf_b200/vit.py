@@ -105,6 +105,16 @@ class VitEngine:
         self._ws = None
         self._finalizer = weakref.finalize(self, load().vittf_vit_destroy, handle)
 
+    def timing(self, enable):
+        check(load().vittf_vit_timing_enable(self._handle, int(enable)), "vittf_vit_timing_enable")
+
+    def read_timing(self):
+        """{'attention': (ms, launches), 'gemm': (ms, launches)} since the last read (synchronises)."""
+        ms = (C.c_double * 2)()
+        n = (C.c_int64 * 2)()
+        check(load().vittf_vit_timing_read(self._handle, ms, n), "vittf_vit_timing_read")
+        return {"attention": (ms[0], n[0]), "gemm": (ms[1], n[1])}
+
     def pos_for(self, im0, im1):
         key = (im0, im1)
         if key not in self._pos_cache:
