@@ -68,7 +68,7 @@ int vittf_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank
         vittf_set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
         return VITTF_ERR_CUDA;
     }
-    VITTF_REQUIRE(elem_bytes == 2, "vittf_make_tmap: only 16-bit elements supported");
+    VITTF_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "vittf_make_tmap: only 16-bit and fp32 elements supported");
     VITTF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "vittf_make_tmap: base pointer must be 16-byte aligned");
     cuuint64_t gdims[5];
     cuuint64_t gstrides[4];
@@ -84,7 +84,8 @@ int vittf_make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank
             gstrides[i - 1] = strides_bytes[i - 1];
         }
     }
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
+    CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                    static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
                     gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

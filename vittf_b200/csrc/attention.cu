@@ -4,13 +4,17 @@
 //
 // B200 design (one CTA per 256 query rows of one (image, head), 384 threads):
 //   warp 0    : TMA producer -- Q tiles once, then a 3-stage ring of K (128x64) and V^T (64x128) tiles
-//   warp 1    : MMA issuer   -- S = Q K^T (tcgen05.mma SS, 128x128x16, fp32 in TMEM), O += P V (tcgen05.mma TS:
-//                               P is read straight from TMEM, V^T from smem), for two query tiles ping-pong
-//   warp 2    : TMEM allocator (S_A, S_B: 2 x 128 cols; O_A, O_B: 2 x 64 cols; P aliases S)
+//   warp 1    : MMA issuer   -- S = Q K^T (tcgen05.mma SS, 128x128x16, fp32 in TMEM), O += P [V | 1] (tcgen05.mma TS:
+//                               P is read straight from TMEM, V^T from smem), for two query tiles ping-pong.
+//                               A constant "ones" row appended to every V^T tile makes the tensor core produce the
+//                               softmax denominator in accumulator column 64 -- no per-element adds on the CUDA cores.
+//   warp 2    : TMEM allocator (S_A, S_B: 2 x 128 cols; O_A, O_B: 2 x 80 cols; P aliases S)
 //   warps 4-7 : softmax of query tile A, one score row per thread (tcgen05.ld 32x32b), online max with lazy
 //   warps 8-11: softmax of query tile B  rescaling of O (only when the row max grows by > 2^8), P written back
 //                                         to TMEM as packed bf16.
 // The tensor pipe works on tile B while the CUDA cores do the exponentials of tile A and vice versa.
+// The exponentials are the bound at head dim 64 (16 MUFU/clk/SM vs 4096 MAC/clk/SM): everything else in the
+// softmax loop is trimmed to packed / 3-input instructions (FFMA2, FMNMX3) with short dependency chains.
 #include "common.cuh"
 
 namespace {
@@ -18,16 +22,19 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
+constexpr int NV = HD + 16;                       // V^T rows + the ones row (+15 zero rows): MMA N = 80
 constexpr int KV_STAGES = 3;
 constexpr int ATT_THREADS = 384;
 constexpr int Q_TILE_BYTES = BQ * HD * 2;        // 16 KB
 constexpr int K_TILE_BYTES = BKV * HD * 2;       // 16 KB
-constexpr int V_HALF_BYTES = HD * 64 * 2;        // 8 KB: 64 d-rows x 64 keys
-constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;
+constexpr int V_ROWS_BYTES = HD * 64 * 2;        // 8 KB: 64 d-rows x 64 keys
+constexpr int ONES_BYTES = 16 * 64 * 2;          // 2 KB: 16 rows x 64 keys
+constexpr int V_HALF_BYTES = V_ROWS_BYTES + ONES_BYTES;   // 10 KB, rows 64..79 follow rows 0..63 (8-row groups 1 KB apart)
+constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;   // 36 KB
 constexpr int ATT_SMEM_BYTES = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
 constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0;     // + t*128
-constexpr int COL_O = 256;   // + t*64
+constexpr int COL_O = 256;   // + t*128 (80 columns used: 64 outputs, column 64 = row sum)
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 struct AttnParams {
@@ -35,6 +42,25 @@ struct AttnParams {
     int tokens, heads, D;
     float scale_log2e;
 };
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// (x0, x1) = (s0, s1) * c + nm   -- one packed FFMA2
+__device__ __forceinline__ void ffma2(float& x0, float& x1, float s0, float s1, float c, float nm) {
+    asm("{\n"
+        ".reg .b64 ra, rb, rc, rd;\n"
+        "mov.b64 ra, {%2, %3};\n"
+        "mov.b64 rb, {%4, %4};\n"
+        "mov.b64 rc, {%5, %5};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n"
+        "mov.b64 {%0, %1}, rd;\n"
+        "}\n"
+        : "=f"(x0), "=f"(x1)
+        : "f"(s0), "f"(s1), "f"(c), "f"(nm));
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, AttnParams p) {
@@ -73,10 +99,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (warp == 3) {
+        // constant rows 64..79 of every V^T half tile: row 64 = 1.0 (bf16 0x3F80), rows 65..79 = 0.  Every row
+        // is constant, so the 128-byte swizzle permutation inside a row does not matter.
+        for (int i = lane; i < KV_STAGES * 2 * (ONES_BYTES / 16); i += 32) {
+            const int tile = i / (ONES_BYTES / 16), chunk = i % (ONES_BYTES / 16);   // 16-byte chunks, 8 per row
+            const uint32_t v = (chunk < 8) ? 0x3F803F80u : 0u;
+            uint8_t* base = s_kv + (tile >> 1) * KV_STAGE_BYTES + K_TILE_BYTES + (tile & 1) * V_HALF_BYTES + V_ROWS_BYTES;
+            *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(v, v, v, v);
+        }
+        ptx::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+
+    // register re-balancing: the producer / MMA / allocator warpgroup needs few registers, the two softmax
+    // warpgroups hold a whole 128-wide score row per thread
+    if (warp < 4) ptx::setmaxnreg_dec<64>();
+    else ptx::setmaxnreg_inc<216>();
 
     if (threadIdx.x == 0) {
         // ---------------- TMA producer ----------------
@@ -90,7 +132,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             const int st = j % KV_STAGES;
             ptx::mbar_wait(&kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
             uint8_t* dst = s_kv + st * KV_STAGE_BYTES;
-            ptx::mbar_arrive_expect_tx(&kv_full[st], KV_STAGE_BYTES);
+            ptx::mbar_arrive_expect_tx(&kv_full[st], K_TILE_BYTES + 2 * V_ROWS_BYTES);
             ptx::tma_load_3d(dst, &tm_qk, &kv_full[st], p.D + head * HD, j * BKV, img);
             ptx::tma_load_2d(dst + K_TILE_BYTES, &tm_vt, &kv_full[st], j * BKV, vt_row);
             ptx::tma_load_2d(dst + K_TILE_BYTES + V_HALF_BYTES, &tm_vt, &kv_full[st], j * BKV + 64, vt_row);
@@ -98,7 +140,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     } else if (threadIdx.x == 32) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BQ, BKV);
-        constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, HD);
+        constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, NV);
         const uint32_t q_addr = ptx::smem_u32(s_q);
         const uint32_t kv_addr = ptx::smem_u32(s_kv);
         auto issue_s = [&](int t, int st) {
@@ -114,7 +156,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             for (int ks = 0; ks < BKV / 16; ++ks) {
                 const uint64_t bdesc = ptx::smem_desc_k_sw128(v_addr + (ks >> 2) * V_HALF_BYTES) + 2 * (ks & 3);
                 // P: packed bf16 pairs, 8 TMEM columns per 16 keys
-                ptx::umma_ts(tmem_base + COL_O + t * 64, tmem_base + COL_S + t * 128 + ks * 8, bdesc, idesc_o,
+                ptx::umma_ts(tmem_base + COL_O + t * 128, tmem_base + COL_S + t * 128 + ks * 8, bdesc, idesc_o,
                              acc || ks != 0);
             }
         };
@@ -151,10 +193,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             const int q = warp & 3;
             const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
             const uint32_t t_s = tmem_base + lane_base + COL_S + t * 128;
-            const uint32_t t_o = tmem_base + lane_base + COL_O + t * 64;
+            const uint32_t t_o = tmem_base + lane_base + COL_O + t * 128;
             const float c = p.scale_log2e;
             float m_used = -INFINITY;
-            float l = 0.0f;
             for (int j = 0; j < nkv; ++j) {
                 ptx::mbar_wait(&s_full[t], j & 1);
                 ptx::tc_fence_after();
@@ -170,12 +211,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                         for (int i = 0; i < 32; ++i)
                             if (ch * 32 + i >= valid) s[ch][i] = 0xff800000u;  // -inf
                 }
-                float mx = -INFINITY;
+                // row max: 8 independent chains of 3-input max
+                float mx[8];
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
+                for (int a = 0; a < 8; ++a) mx[a] = __uint_as_float(s[a >> 1][(a & 1) * 16]);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[ch][i]));
-                const float m_blk = mx * c;
+                for (int a = 0; a < 8; ++a) {
+                    const uint32_t* sv = &s[a >> 1][(a & 1) * 16];
+#pragma unroll
+                    for (int i = 1; i < 15; i += 2) mx[a] = max3(mx[a], __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+                    mx[a] = fmaxf(mx[a], __uint_as_float(sv[15]));
+                }
+                const float m_blk = max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * c;
                 const bool grow = m_blk > m_used + RESCALE_THRESHOLD;
                 if (__any_sync(0xffffffffu, grow)) {
                     const float m_new = grow ? m_blk : m_used;
@@ -190,24 +237,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
                             ptx::tmem_st32(t_o + h * 32, o);
                         }
+                        uint32_t l16[16];                       // column 64 = running denominator
+                        ptx::tmem_ld16(t_o + 64, l16);
+                        ptx::tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) l16[i] = __float_as_uint(__uint_as_float(l16[i]) * f);
+                        ptx::tmem_st16(t_o + 64, l16);
                     }
-                    l *= f;
                     m_used = m_new;
                 }
-                float sum = 0.0f;
+                const float nm = -m_used;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(s[ch][2 * i]), c, -m_used));
-                        const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(s[ch][2 * i + 1]), c, -m_used));
-                        sum += p0 + p1;
-                        pk[i] = ptx::pack_bf16x2(p0, p1);
+                        float x0, x1;
+                        ffma2(x0, x1, __uint_as_float(s[ch][2 * i]), __uint_as_float(s[ch][2 * i + 1]), c, nm);
+                        pk[i] = ptx::pack_bf16x2(ptx::ex2_approx(x0), ptx::ex2_approx(x1));
                     }
                     ptx::tmem_st16(t_s + ch * 16, pk);  // P aliases the first 64 columns of S (row-private)
                 }
-                l += sum;
                 ptx::tc_wait_st();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&p_ready[t]);
@@ -216,7 +266,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             ptx::mbar_wait(o_final, 0);
             ptx::tc_fence_after();
             const int row = q0 + t * BQ + q * 32 + lane;
-            const float inv = 1.0f / l;
+            uint32_t l16[16];
+            ptx::tmem_ld16(t_o + 64, l16);
+            ptx::tc_wait_ld();
+            const float inv = 1.0f / __uint_as_float(l16[0]);
             __nv_bfloat16* dst = p.out + (static_cast<size_t>(img) * p.tokens + row) * p.D + head * HD;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {

@@ -2,10 +2,14 @@
 // that /root/reference/infer.py:177 runs): C = A W^T + bias with fused epilogues.
 //
 // B200 design: persistent, warp-specialised kernel, one CTA per SM.
-//   warp 0  : TMA producer  (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 bf16 tiles, STAGES-deep ring)
-//   warp 1  : MMA issuer    (one thread, tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16, fp32 accum in TMEM)
-//   warp 2  : TMEM allocator
-//   warps 4-7: epilogue     (tcgen05.ld 32x32b, one accumulator row per thread, bias / GELU / residual / split)
+//   warp 0    : TMA producer  (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 bf16 tiles, STAGES-deep ring)
+//   warp 1    : MMA issuer    (one thread, tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warp 2    : TMEM allocator
+//   warps 4-11: epilogue      (tcgen05.ld 32x32b, one accumulator row per thread; two warps per TMEM lane
+//                              quarter, each owning half of the tile's columns).  Results are staged in a
+//                              128B-swizzled shared-memory tile per warp and leave the SM as TMA tile stores;
+//                              the residual update x += A W^T + b is a TMA reduce-add (the read-modify-write
+//                              happens in L2, the SM never reads the fp32 residual stream).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1 -- essential here because K is short (384..3072).
 #include "common.cuh"
@@ -14,16 +18,20 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int STAGING_BYTES = 32 * 128;  // one 32-row x 128-byte tile per epilogue warp
 
 template <int BN>
 struct GemmCfg {
     static constexpr int STAGES = BN <= 128 ? 6 : 4;
+    static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;   // TMEM column offset of the second accumulator
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+    static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 1024 + 512;
 };
 
 struct GemmParams {
@@ -34,86 +42,52 @@ struct GemmParams {
     int tokens, tok_pad, heads;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), erf from Abramowitz-Stegun 7.1.28
+//   erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16,  |err| <= 3e-7  (far below the bf16 output rounding),
+// evaluated on PAIRS of values with packed fp32x2 instructions (FFMA2 / FMUL2): ~10 issue slots and one
+// MUFU.RCP per element instead of the ~30 instructions of erff(), so the fc1 epilogue hides under the MMAs.
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_make(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_get(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// Epilogue for 32 consecutive accumulator columns [n, n+32) of one row.
-template <int EPI>
-__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int n, const uint32_t (&acc)[32]) {
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-        v[i + 0] = __uint_as_float(acc[i + 0]) + b.x;
-        v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
-        v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
-        v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
-    }
-    if (row >= p.M) return;
-    if constexpr (EPI == VITTF_EPI_BIAS_BF16 || EPI == VITTF_EPI_BIAS_GELU_BF16) {
-        if constexpr (EPI == VITTF_EPI_BIAS_GELU_BF16) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.N + n);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            dst[i] = make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-    } else if constexpr (EPI == VITTF_EPI_BIAS_RESID_F32) {
-        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.N + n);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 r = dst[i];
-            r.x += v[4 * i + 0];
-            r.y += v[4 * i + 1];
-            r.z += v[4 * i + 2];
-            r.w += v[4 * i + 3];
-            dst[i] = r;
-        }
-    } else if constexpr (EPI == VITTF_EPI_QKV_SPLIT) {
-        const int two_d = (p.N / 3) * 2;
-        if (n < two_d) {  // Q and K thirds stay token-major
-            uint4* dst =
-                reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * two_d + n);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                dst[i] =
-                    make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                               ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-        } else {  // V third is stored transposed per (image, head): vt[(b*heads+h)*64 + d][token]
-            const int img = row / p.tokens;
-            const int tok = row - img * p.tokens;
-            const int dcol = n - two_d;  // head*64 + d
-            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out2) +
-                                 (static_cast<size_t>(img) * p.heads * 64 + dcol) * p.tok_pad + tok;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(i) * p.tok_pad] = __float2bfloat16_rn(v[i]);
-        }
-    } else if constexpr (EPI == VITTF_EPI_KFEAT_F16) {
-        const int img = row / p.tokens;
-        const int tok = row - img * p.tokens;
-        if (tok == 0) return;  // CLS dropped (infer.py:202 `[:, 1:]`)
-        const size_t orow = static_cast<size_t>(img) * (p.tokens - 1) + (tok - 1);
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + orow * p.N + n);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __half2 h0 = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
-            __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
-            __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
-            __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
-            dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-        }
-    }
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    const F2 x = f2_make(x0, x1);
+    const F2 ax = f2_make(fabsf(x0), fabsf(x1));
+    const F2 z = f2_mul(ax, f2_make(0.70710678118654752f, 0.70710678118654752f));
+    F2 p = f2_fma(f2_make(0.0000430638f, 0.0000430638f), z, f2_make(0.0002765672f, 0.0002765672f));
+    p = f2_fma(p, z, f2_make(0.0001520143f, 0.0001520143f));
+    p = f2_fma(p, z, f2_make(0.0092705272f, 0.0092705272f));
+    p = f2_fma(p, z, f2_make(0.0422820123f, 0.0422820123f));
+    p = f2_fma(p, z, f2_make(0.0705230784f, 0.0705230784f));
+    p = f2_fma(p, z, f2_make(1.0f, 1.0f));
+    float p0, p1;
+    f2_get(p, p0, p1);
+    F2 r = f2_make(rcp_approx(p0), rcp_approx(p1));
+    r = f2_mul(r, r);
+    r = f2_mul(r, r);
+    r = f2_mul(r, r);
+    r = f2_mul(r, r);                                                      // p^-16 = 1 - erf
+    const F2 erfv = f2_fma(r, f2_make(-1.0f, -1.0f), f2_make(1.0f, 1.0f));
+    const F2 half = f2_make(0.5f, 0.5f);
+    const F2 g = f2_fma(f2_mul(ax, half), erfv, f2_mul(x, half));          // 0.5 (x + |x| erf(|x| / sqrt 2))
+    f2_get(g, x0, x1);
 }
+
+// byte offset of 16-byte chunk `chunk` of row `row` inside a 128B-swizzled 32 x 128 B staging tile
+__device__ __forceinline__ uint32_t swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, GemmParams p) {
+    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                     const __grid_constant__ CUtensorMap tm_out, GemmParams p) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * STAGING_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + Cfg::STAGES;
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
@@ -134,7 +108,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full[i], 1);
-            ptx::mbar_init(&tmem_empty[i], 128);
+            ptx::mbar_init(&tmem_empty[i], EPI_THREADS);
         }
         ptx::fence_barrier_init();
     }
@@ -171,7 +145,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int as = it & 1;
             ptx::mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * BN;
+            const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
             for (int kb = 0; kb < num_kb; ++kb) {
                 ptx::mbar_wait(&full[stage], phase);
                 ptx::tc_fence_after();
@@ -188,25 +162,141 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
     } else if (warp >= 4) {
         // ---------------- epilogue ----------------
-        const int q = warp & 3;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;       // which half of the tile's columns
+        uint8_t* stg = staging + (warp - 4) * STAGING_BYTES;
+        constexpr int CHUNKS = BN / 2 / 32;
+        if (lane == 0) ptx::prefetch_tmap(&tm_out);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
             const int as = it & 1;
+            const int row0 = m_blk * BM + q * 32;
+            const int row = row0 + lane;
+            const int n0 = n_blk * BN + half * (BN / 2);
             ptx::mbar_wait(&tmem_full[as], (it >> 1) & 1);
             ptx::tc_fence_after();
-            const int row = m_blk * BM + q * 32 + lane;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE + half * (BN / 2);
+            // stage_out(): the 32 x 128 B tile in `stg` is complete -> hand it to the TMA engine
+            auto stage_out = [&](int col, bool reduce) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (reduce) ptx::tma_reduce_add_2d(&tm_out, stg, col, row0);
+                    else ptx::tma_store_2d(&tm_out, stg, col, row0);
+                    ptx::bulk_commit();
+                }
+            };
+            auto staging_free = [&]() {          // previous TMA of this warp has finished reading `stg`
+                if (lane == 0) ptx::bulk_wait_read<0>();
+                __syncwarp();
+            };
+            auto load_biased = [&](int c, float (&v)[32]) {
                 uint32_t acc[32];
                 ptx::tmem_ld32(taddr + c * 32, acc);
                 ptx::tc_wait_ld();
-                epilogue_store<EPI>(p, row, n_blk * BN + c * 32, acc);
+                const int n = n0 + c * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                    v[i + 0] = __uint_as_float(acc[i + 0]) + b.x;
+                    v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
+                    v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
+                    v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+                }
+            };
+            auto put_bf16 = [&](int chunk0, const float (&v)[32]) {   // 32 values -> 4 chunks of 8 bf16
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<uint4*>(stg + swz(lane, chunk0 + i)) =
+                        make_uint4(ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]), ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            };
+
+            if constexpr (EPI == VITTF_EPI_BIAS_RESID_F32) {
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+                    float v[32];
+                    load_biased(c, v);
+                    if (c == CHUNKS - 1) {       // accumulator fully read: give it back to the MMA warp
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&tmem_empty[as]);
+                    }
+                    staging_free();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(stg + swz(lane, i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    stage_out(n0 + c * 32, true);
+                }
+            } else if constexpr (EPI == VITTF_EPI_BIAS_BF16 || EPI == VITTF_EPI_BIAS_GELU_BF16 || EPI == VITTF_EPI_QKV_SPLIT) {
+                static_assert(CHUNKS % 2 == 0, "bf16 epilogues stage 64-column tiles");
+                const int two_d = (p.N / 3) * 2;
+#pragma unroll
+                for (int c = 0; c < CHUNKS; c += 2) {
+                    float v0[32], v1[32];
+                    load_biased(c, v0);
+                    load_biased(c + 1, v1);
+                    if (c == CHUNKS - 2) {
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&tmem_empty[as]);
+                    }
+                    const int n = n0 + c * 32;
+                    if (EPI == VITTF_EPI_QKV_SPLIT && n >= two_d) {
+                        // V third: stored transposed per (image, head): vt[(img*heads+h)*64 + d][token]; lanes hold
+                        // consecutive tokens, so each store instruction writes 64 contiguous bytes
+                        if (row < p.M) {
+                            const int img = row / p.tokens;
+                            const int tok = row - img * p.tokens;
+                            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out2) +
+                                                 (static_cast<size_t>(img) * p.heads * 64 + (n - two_d)) * p.tok_pad + tok;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(i) * p.tok_pad] = __float2bfloat16_rn(v0[i]);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(32 + i) * p.tok_pad] = __float2bfloat16_rn(v1[i]);
+                        }
+                        continue;
+                    }
+                    if constexpr (EPI == VITTF_EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            gelu_erf2(v0[i], v0[i + 1]);
+                            gelu_erf2(v1[i], v1[i + 1]);
+                        }
+                    }
+                    staging_free();
+                    put_bf16(0, v0);
+                    put_bf16(4, v1);
+                    stage_out(n, false);
+                }
+            } else {  // VITTF_EPI_KFEAT_F16: CLS rows dropped (infer.py:202 `[:, 1:]`), fp16, direct stores
+                const int img = row / p.tokens;
+                const int tok = row - img * p.tokens;
+                const bool live = row < p.M && tok != 0;
+                const size_t orow = static_cast<size_t>(img) * (p.tokens - 1) + (tok - 1);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+                    float v[32];
+                    load_biased(c, v);
+                    if (c == CHUNKS - 1) {
+                        ptx::tc_fence_before();
+                        ptx::mbar_arrive(&tmem_empty[as]);
+                    }
+                    if (live) {
+                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + orow * p.N + n0 + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __half2 h0 = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
+                            __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+                            __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
+                            __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+                            dst[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+                        }
+                    }
+                }
             }
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&tmem_empty[as]);
         }
+        if (lane == 0) ptx::bulk_wait_all();       // staging tiles must outlive their TMA reads; writes complete
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -216,7 +306,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 template <int BN, int EPI>
 int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    CUtensorMap tm_a, tm_b;
+    CUtensorMap tm_a, tm_b, tm_out;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
         uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
@@ -229,6 +319,20 @@ int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t 
         uint32_t box[2] = {BK, BN};
         VITTF_CHECK(vittf_make_tmap(&tm_b, W, 2, 2, dims, strides, box, true));
     }
+    if (EPI == VITTF_EPI_BIAS_RESID_F32) {            // fp32 (M, N), 32 x 32 tiles, reduce-add
+        uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+        uint64_t strides[1] = {static_cast<uint64_t>(p.N) * 4};
+        uint32_t box[2] = {32, 32};
+        VITTF_CHECK(vittf_make_tmap(&tm_out, p.out, 4, 2, dims, strides, box, true));
+    } else if (EPI == VITTF_EPI_KFEAT_F16) {
+        tm_out = tm_a;                                // unused by this epilogue
+    } else {                                          // bf16 (M, ldc), 64 x 32 tiles
+        const uint64_t ldc = EPI == VITTF_EPI_QKV_SPLIT ? static_cast<uint64_t>(p.N / 3) * 2 : static_cast<uint64_t>(p.N);
+        uint64_t dims[2] = {ldc, static_cast<uint64_t>(p.M)};
+        uint64_t strides[1] = {ldc * 2};
+        uint32_t box[2] = {64, 32};
+        VITTF_CHECK(vittf_make_tmap(&tm_out, p.out, 2, 2, dims, strides, box, true));
+    }
     auto kern = gemm_bf16_kernel<BN, EPI>;
     static bool configured = false;
     if (!configured) {
@@ -237,7 +341,7 @@ int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t 
     }
     const int tiles = ceil_div(p.M, BM) * (p.N / BN);
     const int grid = tiles < vittf_num_sms() ? tiles : vittf_num_sms();
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, tm_out, p);
     VITTF_CHECK_CUDA(cudaGetLastError());
     vittf_count_launches(1);
     return VITTF_OK;
@@ -253,20 +357,31 @@ extern "C" int vittf_gemm_bf16(const void* A, const void* W, const float* bias, 
     VITTF_REQUIRE(N % 128 == 0, "vittf_gemm_bf16: N=%d must be a multiple of 128", N);
     GemmParams p{bias, out, out2, M, N, K, tokens, tok_pad, 0};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // widest tile that divides N (a wider tile halves the shared-memory operand traffic per MMA); the bf16
+    // epilogues stage 64-column tiles per warp, so they use 256 or 128; the fp32 reduce-add also takes 192
+#define VITTF_GEMM_BF16OUT(E)                                             \
+    do {                                                                  \
+        if (N % 256 == 0) return launch_gemm<256, E>(A, W, p, s);         \
+        return launch_gemm<128, E>(A, W, p, s);                           \
+    } while (0)
     switch (epi) {
-        case VITTF_EPI_BIAS_BF16: return launch_gemm<128, VITTF_EPI_BIAS_BF16>(A, W, p, s);
-        case VITTF_EPI_BIAS_GELU_BF16: return launch_gemm<128, VITTF_EPI_BIAS_GELU_BF16>(A, W, p, s);
-        case VITTF_EPI_BIAS_RESID_F32: return launch_gemm<128, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
+        case VITTF_EPI_BIAS_BF16: VITTF_GEMM_BF16OUT(VITTF_EPI_BIAS_BF16);
+        case VITTF_EPI_BIAS_GELU_BF16: VITTF_GEMM_BF16OUT(VITTF_EPI_BIAS_GELU_BF16);
+        case VITTF_EPI_BIAS_RESID_F32:
+            if (N % 256 == 0) return launch_gemm<256, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
+            if (N % 192 == 0) return launch_gemm<192, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
+            return launch_gemm<128, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
         case VITTF_EPI_QKV_SPLIT:
             VITTF_REQUIRE(out2 && N % 3 == 0 && (N / 3) % 64 == 0 && tokens > 0 && tok_pad >= tokens && M % tokens == 0,
                           "vittf_gemm_bf16: bad QKV split arguments (N=%d tokens=%d tok_pad=%d M=%d)", N, tokens,
                           tok_pad, M);
             p.heads = N / 3 / 64;
-            return launch_gemm<128, VITTF_EPI_QKV_SPLIT>(A, W, p, s);
+            VITTF_GEMM_BF16OUT(VITTF_EPI_QKV_SPLIT);
         case VITTF_EPI_KFEAT_F16:
             VITTF_REQUIRE(tokens > 1 && M % tokens == 0, "vittf_gemm_bf16: bad K-feature arguments");
             return launch_gemm<128, VITTF_EPI_KFEAT_F16>(A, W, p, s);
         default: VITTF_REQUIRE(false, "vittf_gemm_bf16: unknown epilogue %d", epi);
     }
+#undef VITTF_GEMM_BF16OUT
     return VITTF_OK;
 }
