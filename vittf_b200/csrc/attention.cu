@@ -62,6 +62,29 @@ __device__ __forceinline__ void ffma2(float& x0, float& x1, float s0, float s1, 
         : "f"(s0), "f"(s1), "f"(c), "f"(nm));
 }
 
+// 2^x for a pair of values WITHOUT the MUFU pipe (Cody-Waite range reduction + degree-3 polynomial on the
+// FMA pipe, relative error 8e-5 -- invisible after the bf16 rounding of P).  Used for a fixed fraction of the
+// exponentials so that the 16/clk/SM MUFU unit and the FMA pipes work side by side.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+    const float magic = 12582912.0f;                       // 1.5 * 2^23: adding it rounds to the nearest integer
+    x0 = fmaxf(x0, -126.0f);                               // -inf (masked keys) / deep underflow -> 2^-126 ~ 0
+    x1 = fmaxf(x1, -126.0f);
+    const ptx::F2 x = ptx::f2_make(x0, x1);
+    const ptx::F2 t = ptx::f2_add(x, ptx::f2_make(magic, magic));
+    const ptx::F2 n = ptx::f2_add(t, ptx::f2_make(-magic, -magic));
+    const ptx::F2 fr = ptx::f2_fma(n, ptx::f2_make(-1.0f, -1.0f), x);            // x - round(x) in [-0.5, 0.5]
+    ptx::F2 q = ptx::f2_fma(fr, ptx::f2_make(0.05508868f, 0.05508868f), ptx::f2_make(0.24260405f, 0.24260405f));
+    q = ptx::f2_fma(q, fr, ptx::f2_make(0.69327623f, 0.69327623f));
+    q = ptx::f2_fma(q, fr, ptx::f2_make(0.99992895f, 0.99992895f));
+    float t0, t1, q0, q1;
+    ptx::f2_get(t, t0, t1);
+    ptx::f2_get(q, q0, q1);
+    // add round(x) to the exponent field: the integer sits in the low mantissa bits of t
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+constexpr int POLY_EVERY = 0;   // every POLY_EVERY-th pair of exponentials runs on the FMA pipe (0 = none)
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -77,7 +100,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     uint64_t* o_final = p_ready + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
     const int lane = threadIdx.x & 31;
     const int unit = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
     const int q0 = unit * 2 * BQ;
@@ -85,7 +108,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     const int n_tiles = has_b ? 2 : 1;
     const int nkv = (p.tokens + BKV - 1) / BKV;
 
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {   // one-time setup, not on the hot path
         ptx::mbar_init(q_full, 1);
         for (int i = 0; i < KV_STAGES; ++i) {
             ptx::mbar_init(&kv_full[i], 1);
@@ -117,27 +140,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 
     // register re-balancing: the producer / MMA / allocator warpgroup needs few registers, the two softmax
     // warpgroups hold a whole 128-wide score row per thread
-    if (warp < 4) ptx::setmaxnreg_dec<64>();
-    else ptx::setmaxnreg_inc<216>();
+    // (each role region below is entered right after its own setmaxnreg so that ptxas sees the budget)
 
-    if (threadIdx.x == 0) {
-        // ---------------- TMA producer ----------------
-        ptx::prefetch_tmap(&tm_qk);
-        ptx::prefetch_tmap(&tm_vt);
-        ptx::mbar_arrive_expect_tx(q_full, n_tiles * Q_TILE_BYTES);
-        for (int t = 0; t < n_tiles; ++t)
-            ptx::tma_load_3d(s_q + t * Q_TILE_BYTES, &tm_qk, q_full, head * HD, q0 + t * BQ, img);
-        const int vt_row = (img * p.heads + head) * HD;
-        for (int j = 0; j < nkv; ++j) {
-            const int st = j % KV_STAGES;
-            ptx::mbar_wait(&kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
-            uint8_t* dst = s_kv + st * KV_STAGE_BYTES;
-            ptx::mbar_arrive_expect_tx(&kv_full[st], K_TILE_BYTES + 2 * V_ROWS_BYTES);
-            ptx::tma_load_3d(dst, &tm_qk, &kv_full[st], p.D + head * HD, j * BKV, img);
-            ptx::tma_load_2d(dst + K_TILE_BYTES, &tm_vt, &kv_full[st], j * BKV, vt_row);
-            ptx::tma_load_2d(dst + K_TILE_BYTES + V_HALF_BYTES, &tm_vt, &kv_full[st], j * BKV + 64, vt_row);
+    // Roles are dispatched per WARP (uniform) and the single issuing lane is chosen with elect.sync: a branch on
+    // threadIdx.x would make ptxas wrap every TMA / MMA instruction in a divergence ("waterfall") loop, because
+    // their descriptor operands must live in uniform registers.  Only that one lane polls the mbarriers -- a full
+    // warp spinning on try_wait measurably starves the softmax warps that share its scheduler.
+    if (warp < 4) {
+      ptx::setmaxnreg_dec<64>();
+      if (warp == 0) {
+        // ---------------- TMA producer (one elected lane) ----------------
+        if (ptx::elect_one()) {
+            ptx::prefetch_tmap(&tm_qk);
+            ptx::prefetch_tmap(&tm_vt);
+            ptx::mbar_arrive_expect_tx(q_full, n_tiles * Q_TILE_BYTES);
+            for (int t = 0; t < n_tiles; ++t)
+                ptx::tma_load_3d(s_q + t * Q_TILE_BYTES, &tm_qk, q_full, head * HD, q0 + t * BQ, img);
+            const int vt_row = (img * p.heads + head) * HD;
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j % KV_STAGES;
+                ptx::mbar_wait(&kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+                uint8_t* dst = s_kv + st * KV_STAGE_BYTES;
+                ptx::mbar_arrive_expect_tx(&kv_full[st], K_TILE_BYTES + 2 * V_ROWS_BYTES);
+                ptx::tma_load_3d(dst, &tm_qk, &kv_full[st], p.D + head * HD, j * BKV, img);
+                ptx::tma_load_2d(dst + K_TILE_BYTES, &tm_vt, &kv_full[st], j * BKV, vt_row);
+                ptx::tma_load_2d(dst + K_TILE_BYTES + V_HALF_BYTES, &tm_vt, &kv_full[st], j * BKV + 64, vt_row);
+            }
         }
-    } else if (threadIdx.x == 32) {
+      } else if (warp == 1 && ptx::elect_one()) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BQ, BKV);
         constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, NV);
@@ -182,11 +212,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     issue_s(t, (j + 1) % KV_STAGES);
                     ptx::tc_commit(&s_full[t]);  // also certifies that P V of block j is complete
                 }
+                if (t == n_tiles - 1) {
+                    ptx::tc_commit(&kv_empty[st]);
+                    if (!more) ptx::tc_commit(o_final);
+                }
             }
-            ptx::tc_commit(&kv_empty[st]);
         }
-        ptx::tc_commit(o_final);
-    } else if (warp >= 4) {
+      }
+    } else {
+        ptx::setmaxnreg_inc<216>();
         // ---------------- softmax + output ----------------
         const int t = (warp - 4) >> 2;
         if (t < n_tiles) {
@@ -254,7 +288,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     for (int i = 0; i < 16; ++i) {
                         float x0, x1;
                         ffma2(x0, x1, __uint_as_float(s[ch][2 * i]), __uint_as_float(s[ch][2 * i + 1]), c, nm);
-                        pk[i] = ptx::pack_bf16x2(ptx::ex2_approx(x0), ptx::ex2_approx(x1));
+                        if (POLY_EVERY > 0 && (i % POLY_EVERY) == POLY_EVERY - 1) {
+                            float p0, p1;
+                            exp2_poly2(x0, x1, p0, p1);
+                            pk[i] = ptx::pack_bf16x2(p0, p1);
+                        } else {
+                            pk[i] = ptx::pack_bf16x2(ptx::ex2_approx(x0), ptx::ex2_approx(x1));
+                        }
                     }
                     ptx::tmem_st16(t_s + ch * 16, pk);  // P aliases the first 64 columns of S (row-private)
                 }

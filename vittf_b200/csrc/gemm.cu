@@ -46,34 +46,27 @@ struct GemmParams {
 //   erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16,  |err| <= 3e-7  (far below the bf16 output rounding),
 // evaluated on PAIRS of values with packed fp32x2 instructions (FFMA2 / FMUL2): ~10 issue slots and one
 // MUFU.RCP per element instead of the ~30 instructions of erff(), so the fc1 epilogue hides under the MMAs.
-struct F2 { unsigned long long v; };
-__device__ __forceinline__ F2 f2_make(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void f2_get(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
-__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
-__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
-    const F2 x = f2_make(x0, x1);
-    const F2 ax = f2_make(fabsf(x0), fabsf(x1));
-    const F2 z = f2_mul(ax, f2_make(0.70710678118654752f, 0.70710678118654752f));
-    F2 p = f2_fma(f2_make(0.0000430638f, 0.0000430638f), z, f2_make(0.0002765672f, 0.0002765672f));
-    p = f2_fma(p, z, f2_make(0.0001520143f, 0.0001520143f));
-    p = f2_fma(p, z, f2_make(0.0092705272f, 0.0092705272f));
-    p = f2_fma(p, z, f2_make(0.0422820123f, 0.0422820123f));
-    p = f2_fma(p, z, f2_make(0.0705230784f, 0.0705230784f));
-    p = f2_fma(p, z, f2_make(1.0f, 1.0f));
+    const ptx::F2 x = ptx::f2_make(x0, x1);
+    const ptx::F2 ax = ptx::f2_make(fabsf(x0), fabsf(x1));
+    const ptx::F2 z = ptx::f2_mul(ax, ptx::f2_make(0.70710678118654752f, 0.70710678118654752f));
+    ptx::F2 p = ptx::f2_fma(ptx::f2_make(0.0000430638f, 0.0000430638f), z, ptx::f2_make(0.0002765672f, 0.0002765672f));
+    p = ptx::f2_fma(p, z, ptx::f2_make(0.0001520143f, 0.0001520143f));
+    p = ptx::f2_fma(p, z, ptx::f2_make(0.0092705272f, 0.0092705272f));
+    p = ptx::f2_fma(p, z, ptx::f2_make(0.0422820123f, 0.0422820123f));
+    p = ptx::f2_fma(p, z, ptx::f2_make(0.0705230784f, 0.0705230784f));
+    p = ptx::f2_fma(p, z, ptx::f2_make(1.0f, 1.0f));
     float p0, p1;
-    f2_get(p, p0, p1);
-    F2 r = f2_make(rcp_approx(p0), rcp_approx(p1));
-    r = f2_mul(r, r);
-    r = f2_mul(r, r);
-    r = f2_mul(r, r);
-    r = f2_mul(r, r);                                                      // p^-16 = 1 - erf
-    const F2 erfv = f2_fma(r, f2_make(-1.0f, -1.0f), f2_make(1.0f, 1.0f));
-    const F2 half = f2_make(0.5f, 0.5f);
-    const F2 g = f2_fma(f2_mul(ax, half), erfv, f2_mul(x, half));          // 0.5 (x + |x| erf(|x| / sqrt 2))
-    f2_get(g, x0, x1);
+    ptx::f2_get(p, p0, p1);
+    ptx::F2 r = ptx::f2_make(ptx::rcp_approx(p0), ptx::rcp_approx(p1));
+    r = ptx::f2_mul(r, r);
+    r = ptx::f2_mul(r, r);
+    r = ptx::f2_mul(r, r);
+    r = ptx::f2_mul(r, r);                                                      // p^-16 = 1 - erf
+    const ptx::F2 erfv = ptx::f2_fma(r, ptx::f2_make(-1.0f, -1.0f), ptx::f2_make(1.0f, 1.0f));
+    const ptx::F2 half = ptx::f2_make(0.5f, 0.5f);
+    const ptx::F2 g = ptx::f2_fma(ptx::f2_mul(ax, half), erfv, ptx::f2_mul(x, half));          // 0.5 (x + |x| erf(|x| / sqrt 2))
+    ptx::f2_get(g, x0, x1);
 }
 
 // byte offset of 16-byte chunk `chunk` of row `row` inside a 128B-swizzled 32 x 128 B staging tile
@@ -94,7 +87,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
     const int lane = threadIdx.x & 31;
     const int m_tiles = (p.M + BM - 1) / BM;
     const int n_tiles = p.N / BN;
@@ -118,7 +111,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (threadIdx.x == 0) {
+    // Roles are dispatched per WARP (uniform) and the issuing lane is chosen with elect.sync: a branch on
+    // threadIdx.x would make ptxas wrap every TMA / MMA instruction in a divergence ("waterfall") loop.
+    // Only that one lane polls the mbarriers.
+    if (warp == 0 && ptx::elect_one()) {
         // ---------------- TMA producer ----------------
         ptx::prefetch_tmap(&tm_a);
         ptx::prefetch_tmap(&tm_b);
@@ -135,7 +131,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (threadIdx.x == 32) {
+    } else if (warp == 1 && ptx::elect_one()) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN);
         int stage = 0;
@@ -156,9 +152,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 step inside the swizzle row
                     ptx::umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                 ptx::tc_commit(&empty[stage]);
+                if (kb == num_kb - 1) ptx::tc_commit(&tmem_full[as]);
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
-            ptx::tc_commit(&tmem_full[as]);
         }
     } else if (warp >= 4) {
         // ---------------- epilogue ----------------
@@ -166,7 +162,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         const int half = (warp - 4) >> 2;       // which half of the tile's columns
         uint8_t* stg = staging + (warp - 4) * STAGING_BYTES;
         constexpr int CHUNKS = BN / 2 / 32;
-        if (lane == 0) ptx::prefetch_tmap(&tm_out);
+        if (ptx::elect_one()) ptx::prefetch_tmap(&tm_out);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
@@ -181,14 +177,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             auto stage_out = [&](int col, bool reduce) {
                 ptx::fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
+                if (ptx::elect_one()) {          // deterministic leader: the same lane commits and waits
                     if (reduce) ptx::tma_reduce_add_2d(&tm_out, stg, col, row0);
                     else ptx::tma_store_2d(&tm_out, stg, col, row0);
                     ptx::bulk_commit();
                 }
             };
             auto staging_free = [&]() {          // previous TMA of this warp has finished reading `stg`
-                if (lane == 0) ptx::bulk_wait_read<0>();
+                if (ptx::elect_one()) ptx::bulk_wait_read<0>();
                 __syncwarp();
             };
             auto load_biased = [&](int c, float (&v)[32]) {
@@ -296,7 +292,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 }
             }
         }
-        if (lane == 0) ptx::bulk_wait_all();       // staging tiles must outlive their TMA reads; writes complete
+        if (ptx::elect_one()) ptx::bulk_wait_all();   // staging tiles must outlive their TMA reads; writes complete
     }
     ptx::tc_fence_before();
     __syncthreads();
