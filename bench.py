@@ -150,12 +150,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="slices per ViT forward (default: per workload)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     size, arch, fos, n_cls, per_cls, batch = WORKLOADS[args.workload]
+    if args.batch > 0:
+        batch = args.batch
     config = {"workload": WORKLOAD_TEXT[args.workload], "volume": f"{size}^3 uint8", "backbone": arch,
               "feature_output_size": fos, "classes": n_cls, "prototypes": n_cls * per_cls, "slice_batch": batch,
               "parallelism": f"slices sharded over {world} GPU(s), z-slab similarity" if world > 1 else "single GPU",

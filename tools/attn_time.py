@@ -1,0 +1,18 @@
+import sys, torch
+sys.path.insert(0, '.')
+from vittf_b200 import ops
+B, tokens, heads = 8, 4097, 6
+D = heads * 64
+qk = torch.randn(B * tokens, 2 * D, device="cuda").bfloat16()
+vt = torch.randn(B * D, ops.tok_pad_of(tokens), device="cuda").bfloat16()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for _ in range(3): ops.attention(qk, vt, B, tokens, heads, ops.tok_pad_of(tokens))
+torch.cuda.synchronize()
+ts = []
+for _ in range(10):
+    flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); ops.attention(qk, vt, B, tokens, heads, ops.tok_pad_of(tokens)); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+import os
+print(os.environ.get("VITTF_LIB", "default"), "median ms", sorted(ts)[5])

@@ -4,17 +4,24 @@
 //
 // B200 design (one CTA per 256 query rows of one (image, head), 384 threads):
 //   warp 0    : TMA producer -- Q tiles once, then a 3-stage ring of K (128x64) and V^T (64x128) tiles
-//   warp 1    : MMA issuer   -- S = Q K^T (tcgen05.mma SS, 128x128x16, fp32 in TMEM), O += P [V | 1] (tcgen05.mma TS:
-//                               P is read straight from TMEM, V^T from smem), for two query tiles ping-pong.
-//                               A constant "ones" row appended to every V^T tile makes the tensor core produce the
-//                               softmax denominator in accumulator column 64 -- no per-element adds on the CUDA cores.
-//   warp 2    : TMEM allocator (S_A, S_B: 2 x 128 cols; O_A, O_B: 2 x 80 cols; P aliases S)
+//   warp 1    : MMA issuer   -- S = Q K^T (tcgen05.mma SS, 128x128x16, fp32 in TMEM), O += P V (tcgen05.mma TS:
+//                               P is read straight from TMEM, V^T from smem), for two query tiles.
+//   warp 2    : TMEM allocator (S_A, S_B: 2 x 128 cols; P_A, P_B: 2 x 64 cols; O_A, O_B: 2 x 64 cols = all 512).
+//               P has its own columns, so a softmax warp hands its S buffer back as soon as the scores are in
+//               registers and the MMA warp computes S(j+1) while the exponentials of block j are still running.
 //   warps 4-7 : softmax of query tile A, one score row per thread (tcgen05.ld 32x32b), online max with lazy
 //   warps 8-11: softmax of query tile B  rescaling of O (only when the row max grows by > 2^8), P written back
 //                                         to TMEM as packed bf16.
-// The tensor pipe works on tile B while the CUDA cores do the exponentials of tile A and vice versa.
-// The exponentials are the bound at head dim 64 (16 MUFU/clk/SM vs 4096 MAC/clk/SM): everything else in the
-// softmax loop is trimmed to packed / 3-input instructions (FFMA2, FMNMX3) with short dependency chains.
+// What bounds the kernel at head dim 64 is the exponential pipe (16 MUFU/clk/SM vs 4096 MAC/clk/SM), so the
+// softmax loop is built around keeping it busy (all measured with clock64 traces on B200):
+//   * the two softmax warps that share an SM sub-partition (tile A / tile B) take strict turns on the
+//     exponential section through named barriers (ping-pong); left alone they drift into lock-step;
+//   * a quarter of the exponentials run as a Cody-Waite + cubic polynomial on the FMA pipe;
+//   * everything else is packed / 3-input instructions (FFMA2, FADD2, FMNMX3) with short dependency chains;
+//   * roles are dispatched per warp with elect.sync so that ptxas keeps TMA/MMA descriptors in uniform registers
+//     (a branch on threadIdx.x cost ~75 cycles per MMA in divergence loops).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -22,19 +29,17 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int NV = HD + 16;                       // V^T rows + the ones row (+15 zero rows): MMA N = 80
 constexpr int KV_STAGES = 3;
 constexpr int ATT_THREADS = 384;
 constexpr int Q_TILE_BYTES = BQ * HD * 2;        // 16 KB
 constexpr int K_TILE_BYTES = BKV * HD * 2;       // 16 KB
-constexpr int V_ROWS_BYTES = HD * 64 * 2;        // 8 KB: 64 d-rows x 64 keys
-constexpr int ONES_BYTES = 16 * 64 * 2;          // 2 KB: 16 rows x 64 keys
-constexpr int V_HALF_BYTES = V_ROWS_BYTES + ONES_BYTES;   // 10 KB, rows 64..79 follow rows 0..63 (8-row groups 1 KB apart)
-constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;   // 36 KB
+constexpr int V_HALF_BYTES = HD * 64 * 2;        // 8 KB: 64 d-rows x 64 keys
+constexpr int KV_STAGE_BYTES = K_TILE_BYTES + 2 * V_HALF_BYTES;   // 32 KB
 constexpr int ATT_SMEM_BYTES = 2 * Q_TILE_BYTES + KV_STAGES * KV_STAGE_BYTES + 1024 + 256;
 constexpr int TMEM_COLS = 512;
 constexpr int COL_S = 0;     // + t*128
-constexpr int COL_O = 256;   // + t*128 (80 columns used: 64 outputs, column 64 = row sum)
+constexpr int COL_P = 256;   // + t*64   packed bf16 pairs
+constexpr int COL_O = 384;   // + t*64
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 struct AttnParams {
@@ -43,6 +48,16 @@ struct AttnParams {
     float scale_log2e;
 };
 
+#ifdef ATTN_TRACE
+__device__ long long g_trace[3 * 40 * 4];
+#define TRACE(role, j, k) do { if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 40) g_trace[((role) * 40 + (j)) * 4 + (k)] = clock64(); } while (0)
+#else
+#define TRACE(role, j, k) do {} while (0)
+#endif
+// named barriers (ids 1..8; 0 is __syncthreads): the two softmax warps that share a scheduler take turns on the
+// exponential pipe
+__device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -83,7 +98,13 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
     p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
     p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
-constexpr int POLY_EVERY = 0;   // every POLY_EVERY-th pair of exponentials runs on the FMA pipe (0 = none)
+#ifndef POLY_EVERY_V
+#define POLY_EVERY_V 4     // measured on B200: 4 (25 %) > 0 > 2
+#endif
+#ifndef HANDOVER_CH
+#define HANDOVER_CH 2      // hand the pipe over after 3 of the 4 column chunks
+#endif
+constexpr int POLY_EVERY = POLY_EVERY_V;   // every POLY_EVERY-th pair of exponentials runs on the FMA pipe (0 = none)
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, AttnParams p) {
@@ -95,9 +116,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* kv_empty = kv_full + KV_STAGES;
-    uint64_t* s_full = kv_empty + KV_STAGES;  // [2]
-    uint64_t* p_ready = s_full + 2;           // [2]
-    uint64_t* o_final = p_ready + 2;
+    uint64_t* s_full = kv_empty + KV_STAGES;  // [2] scores of the next block are in TMEM
+    uint64_t* s_free = s_full + 2;            // [2] all 128 rows of S are in registers
+    uint64_t* p_ready = s_free + 2;           // [2] P written
+    uint64_t* pv_done = p_ready + 2;          // [2] P V finished (P buffer reusable, O stable)
+    uint64_t* o_final = pv_done + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
@@ -116,23 +139,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s_full[i], 1);
+            ptx::mbar_init(&s_free[i], 128);
             ptx::mbar_init(&p_ready[i], 128);
+            ptx::mbar_init(&pv_done[i], 1);
         }
         ptx::mbar_init(o_final, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
-    if (warp == 3) {
-        // constant rows 64..79 of every V^T half tile: row 64 = 1.0 (bf16 0x3F80), rows 65..79 = 0.  Every row
-        // is constant, so the 128-byte swizzle permutation inside a row does not matter.
-        for (int i = lane; i < KV_STAGES * 2 * (ONES_BYTES / 16); i += 32) {
-            const int tile = i / (ONES_BYTES / 16), chunk = i % (ONES_BYTES / 16);   // 16-byte chunks, 8 per row
-            const uint32_t v = (chunk < 8) ? 0x3F803F80u : 0u;
-            uint8_t* base = s_kv + (tile >> 1) * KV_STAGE_BYTES + K_TILE_BYTES + (tile & 1) * V_HALF_BYTES + V_ROWS_BYTES;
-            *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(v, v, v, v);
-        }
-        ptx::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
-    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                 const int st = j % KV_STAGES;
                 ptx::mbar_wait(&kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
                 uint8_t* dst = s_kv + st * KV_STAGE_BYTES;
-                ptx::mbar_arrive_expect_tx(&kv_full[st], K_TILE_BYTES + 2 * V_ROWS_BYTES);
+                ptx::mbar_arrive_expect_tx(&kv_full[st], KV_STAGE_BYTES);
                 ptx::tma_load_3d(dst, &tm_qk, &kv_full[st], p.D + head * HD, j * BKV, img);
                 ptx::tma_load_2d(dst + K_TILE_BYTES, &tm_vt, &kv_full[st], j * BKV, vt_row);
                 ptx::tma_load_2d(dst + K_TILE_BYTES + V_HALF_BYTES, &tm_vt, &kv_full[st], j * BKV + 64, vt_row);
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       } else if (warp == 1 && ptx::elect_one()) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BQ, BKV);
-        constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, NV);
+        constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, HD);
         const uint32_t q_addr = ptx::smem_u32(s_q);
         const uint32_t kv_addr = ptx::smem_u32(s_kv);
         auto issue_s = [&](int t, int st) {
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             for (int ks = 0; ks < BKV / 16; ++ks) {
                 const uint64_t bdesc = ptx::smem_desc_k_sw128(v_addr + (ks >> 2) * V_HALF_BYTES) + 2 * (ks & 3);
                 // P: packed bf16 pairs, 8 TMEM columns per 16 keys
-                ptx::umma_ts(tmem_base + COL_O + t * 128, tmem_base + COL_S + t * 128 + ks * 8, bdesc, idesc_o,
+                ptx::umma_ts(tmem_base + COL_O + t * 64, tmem_base + COL_P + t * 64 + ks * 8, bdesc, idesc_o,
                              acc || ks != 0);
             }
         };
@@ -199,25 +213,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
         for (int j = 0; j < nkv; ++j) {
             const int st = j % KV_STAGES;
-            const bool more = j + 1 < nkv;
-            if (more) {
+            if (j + 1 < nkv) {
                 ptx::mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
-                ptx::tc_fence_after();
+                for (int t = 0; t < n_tiles; ++t) {   // S(j+1) as soon as block j's scores sit in registers
+                    TRACE(2, j, t * 2);
+                    ptx::mbar_wait(&s_free[t], j & 1);
+                    ptx::tc_fence_after();
+                    issue_s(t, (j + 1) % KV_STAGES);
+                    ptx::tc_commit(&s_full[t]);
+                }
             }
             for (int t = 0; t < n_tiles; ++t) {
                 ptx::mbar_wait(&p_ready[t], j & 1);
+                TRACE(2, j, t * 2 + 1);
                 ptx::tc_fence_after();
                 issue_pv(t, st, j > 0);
-                if (more) {
-                    issue_s(t, (j + 1) % KV_STAGES);
-                    ptx::tc_commit(&s_full[t]);  // also certifies that P V of block j is complete
-                }
-                if (t == n_tiles - 1) {
-                    ptx::tc_commit(&kv_empty[st]);
-                    if (!more) ptx::tc_commit(o_final);
-                }
+                ptx::tc_commit(&pv_done[t]);
             }
+            ptx::tc_commit(&kv_empty[st]);
         }
+        ptx::tc_commit(o_final);
       }
     } else {
         ptx::setmaxnreg_inc<216>();
@@ -227,16 +242,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             const int q = warp & 3;
             const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
             const uint32_t t_s = tmem_base + lane_base + COL_S + t * 128;
-            const uint32_t t_o = tmem_base + lane_base + COL_O + t * 128;
+            const uint32_t t_p = tmem_base + lane_base + COL_P + t * 64;
+            const uint32_t t_o = tmem_base + lane_base + COL_O + t * 64;
             const float c = p.scale_log2e;
             float m_used = -INFINITY;
+            float l = 0.0f;
+            // Ping-pong on the exponential (MUFU) pipe: warps 4+q (tile A) and 8+q (tile B) share an SM sub-partition.
+            // Left alone they run their exponentials at the same time (pipe oversubscribed) and their TMEM loads /
+            // row maxima at the same time (pipe idle); strict alternation keeps the pipe busy.
+            const int bar_mine = 1 + q * 2 + t, bar_other = 1 + q * 2 + (t ^ 1);
+            if (has_b && t == 1) named_arrive(bar_other, 64);   // tile A goes first
             for (int j = 0; j < nkv; ++j) {
+                if (q == 0 && lane == 0) TRACE(t, j, 0);
                 ptx::mbar_wait(&s_full[t], j & 1);
+                if (q == 0 && lane == 0) TRACE(t, j, 1);
                 ptx::tc_fence_after();
                 uint32_t s[4][32];
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(t_s + ch * 32, s[ch]);
                 ptx::tc_wait_ld();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&s_free[t]);          // the MMA warp may overwrite S with the next block's scores
                 const int valid = p.tokens - j * BKV;  // >= 1
                 if (valid < BKV) {
 #pragma unroll
@@ -262,6 +288,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     const float m_new = grow ? m_blk : m_used;
                     const float f = ptx::ex2_approx(m_used - m_new);  // 0 on the first block, 1 if unchanged
                     if (j > 0) {
+                        ptx::mbar_wait(&pv_done[t], (j - 1) & 1);     // P V of block j-1 has landed in O
+                        ptx::tc_fence_after();
                         uint32_t o[32];
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -271,16 +299,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
                             ptx::tmem_st32(t_o + h * 32, o);
                         }
-                        uint32_t l16[16];                       // column 64 = running denominator
-                        ptx::tmem_ld16(t_o + 64, l16);
-                        ptx::tc_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) l16[i] = __float_as_uint(__uint_as_float(l16[i]) * f);
-                        ptx::tmem_st16(t_o + 64, l16);
                     }
+                    l *= f;
                     m_used = m_new;
                 }
+                if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);   // P buffer free again (normally long since)
+                if (has_b) named_sync(bar_mine, 64);             // my turn on the exponential pipe
+                if (q == 0 && lane == 0) TRACE(t, j, 2);
                 const float nm = -m_used;
+                ptx::F2 sums[4] = {{0ull}, {0ull}, {0ull}, {0ull}};    // 4 independent packed (2 x fp32) row-sum chains
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                     uint32_t pk[16];
@@ -288,17 +315,28 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     for (int i = 0; i < 16; ++i) {
                         float x0, x1;
                         ffma2(x0, x1, __uint_as_float(s[ch][2 * i]), __uint_as_float(s[ch][2 * i + 1]), c, nm);
+                        float p0, p1;
                         if (POLY_EVERY > 0 && (i % POLY_EVERY) == POLY_EVERY - 1) {
-                            float p0, p1;
                             exp2_poly2(x0, x1, p0, p1);
-                            pk[i] = ptx::pack_bf16x2(p0, p1);
                         } else {
-                            pk[i] = ptx::pack_bf16x2(ptx::ex2_approx(x0), ptx::ex2_approx(x1));
+                            p0 = ptx::ex2_approx(x0);
+                            p1 = ptx::ex2_approx(x1);
                         }
+                        sums[i & 3] = ptx::f2_add(sums[i & 3], ptx::f2_make(p0, p1));
+                        pk[i] = ptx::pack_bf16x2(p0, p1);
                     }
-                    ptx::tmem_st16(t_s + ch * 16, pk);  // P aliases the first 64 columns of S (row-private)
+                    ptx::tmem_st16(t_p + ch * 16, pk);
+                    // hand the exponential pipe to the other tile's warp a little before my last chunk drains
+                    if (ch == HANDOVER_CH && has_b && !(t == 1 && j == nkv - 1)) named_arrive(bar_other, 64);
+                }
+                {
+                    float a0, a1, b0, b1;
+                    ptx::f2_get(ptx::f2_add(sums[0], sums[1]), a0, a1);
+                    ptx::f2_get(ptx::f2_add(sums[2], sums[3]), b0, b1);
+                    l += (a0 + a1) + (b0 + b1);
                 }
                 ptx::tc_wait_st();
+                if (q == 0 && lane == 0) TRACE(t, j, 3);
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&p_ready[t]);
             }
@@ -306,10 +344,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             ptx::mbar_wait(o_final, 0);
             ptx::tc_fence_after();
             const int row = q0 + t * BQ + q * 32 + lane;
-            uint32_t l16[16];
-            ptx::tmem_ld16(t_o + 64, l16);
-            ptx::tc_wait_ld();
-            const float inv = 1.0f / __uint_as_float(l16[0]);
+            const float inv = 1.0f / l;
             __nv_bfloat16* dst = p.out + (static_cast<size_t>(img) * p.tokens + row) * p.D + head * HD;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -368,5 +403,19 @@ extern "C" int vittf_attention(const void* qk, const void* vt, void* out, int B,
     attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tm_qk, tm_vt, p);
     VITTF_CHECK_CUDA(cudaGetLastError());
     vittf_count_launches(1);
+#ifdef ATTN_TRACE
+    if (getenv("VITTF_ATTN_TRACE_DUMP")) {
+        static long long h[3 * 40 * 4];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
+        long long t0 = h[0];
+        for (int r = 0; r < 3; ++r)
+            for (int j = 2; j < 10; ++j) {
+                printf("role %d blk %2d:", r, j);
+                for (int k = 0; k < 4; ++k) printf(" %7lld", h[(r * 40 + j) * 4 + k] - t0);
+                printf("\n");
+            }
+    }
+#endif
     return VITTF_OK;
 }
