@@ -16,5 +16,5 @@ done
 rc=0
 for p in "${pids[@]}"; do wait "$p" || rc=1; done
 [ $rc -eq 0 ] || { echo "build failed"; exit 1; }
-"${NVCC}" -shared -o "${OUT}" "${HERE}"/build/{api,gemm,attention,vit_ops,vit_engine,similarity,bls}.o -lcudart
+"${NVCC}" -gencode arch=compute_100a,code=sm_100a -shared -o "${OUT}" "${HERE}"/build/{api,gemm,attention,vit_ops,vit_engine,similarity,bls}.o -lcudart
 echo "built ${OUT}"
