@@ -31,9 +31,9 @@ sys.path.insert(0, str(ROOT))
 WORKLOADS = {
     # name: (volume size, arch, fos, classes, annotations per class, batch)
     "tiny": (32, "vits8", 8, 4, 2, 8),
-    "cfg1": (128, "vits8", 64, 4, 8, 8),
-    "cfg2": (256, "vits8", 64, 8, 4, 8),
-    "cfg3": (512, "vitb8", 64, 16, 2, 8),
+    "cfg1": (128, "vits8", 64, 4, 8, 32),
+    "cfg2": (256, "vits8", 64, 8, 4, 32),
+    "cfg3": (512, "vitb8", 64, 16, 2, 16),
 }
 WORKLOAD_TEXT = {
     "tiny": "smoke: 32^3 uint8 phantom, ViT-S/8 random init, 64^2 images, 4 classes",

@@ -78,7 +78,9 @@ def test_compute_similarities_with_bilateral_solver(golden):
 
 
 @pytest.mark.parametrize("lr,out_shape,F_,A", [((6, 5, 4), (24, 15, 20), 24, 6), ((16, 16, 16), (64, 64, 64), 96, 8),
-                                               ((8, 8, 8), (8, 8, 8), 32, 3), ((12, 10, 8), (31, 29, 17), 40, 20)])
+                                               ((8, 8, 8), (8, 8, 8), 32, 3), ((12, 10, 8), (31, 29, 17), 40, 20),
+                                               ((8, 8, 8), (16, 16, 16), 32, 5), ((8, 8, 8), (64, 64, 64), 48, 9),
+                                               ((33, 33, 33), (132, 132, 132), 16, 4)])
 def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
     from oracle import similarity as osim, synth
     from vittf_b200.similarity import similarity_maps
