@@ -13,7 +13,7 @@ from vittf_b200.vit import engine_for  # noqa: E402
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 arch = sys.argv[2] if len(sys.argv) > 2 else "vits8"
 dev = torch.device("cuda", 0)
-vol, _ = synth.ct_volume((256, 256, 16), n_shells=8, seed=0)
+vol, _ = synth.ct_volume((256, 256, max(16, batch)), n_shells=8, seed=0)
 v = vol.to(dev)
 model = build_dino(arch, seed=0)
 eng = engine_for(model, dev, max_batch=batch)
