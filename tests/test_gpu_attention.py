@@ -5,7 +5,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("B,tokens,heads,scale", [(1, 65, 6, 1.0), (2, 129, 6, 1.0), (2, 300, 6, 3.0), (1, 1025, 12, 1.0),
+@pytest.mark.parametrize("B,tokens,heads,scale", [(1, 17, 6, 1.0), (1, 65, 6, 1.0), (2, 128, 6, 1.0), (2, 129, 6, 1.0), (1, 144, 6, 2.0), (1, 256, 6, 1.0),
+                                                   (1, 383, 6, 1.0), (2, 300, 6, 3.0), (1, 1025, 12, 1.0),
                                                    (2, 4097, 6, 1.0), (1, 4097, 6, 6.0)])
 def test_attention_matches_torch(B, tokens, heads, scale):
     from vittf_b200 import ops

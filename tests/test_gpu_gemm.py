@@ -70,6 +70,32 @@ def test_gemm_kfeat_drops_cls():
     assert (out.float() - ref).abs().max().item() < 5e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("N", [384, 1152, 1536])
+def test_gemm_activation_resident_variant(N):
+    """M >= 148 row blocks and K <= 384 select the kernel that keeps the activation tile in shared memory."""
+    from vittf_b200 import _lib, ops
+    M, K = 148 * 128 + 77, 384
+    a, w, b = _mk(M, N, K, seed=7)
+    ref = _ref(a, w, b)
+    out = ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_BF16)
+    assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    if N == 1536:
+        g = ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_GELU_BF16)
+        assert (g.float() - torch.nn.functional.gelu(ref)).abs().max().item() < 2e-2
+    if N == 384:
+        x = torch.randn(M, N, device="cuda")
+        want = x + ref
+        ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_RESID_F32, out=x)
+        assert (x - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
+    if N == 1152:
+        tokens = 37
+        Mq = (M // tokens) * tokens
+        qk, vt = ops.gemm_bf16(a[:Mq].contiguous(), w, b, _lib.EPI_QKV_SPLIT, tokens=tokens, tok_pad=128)
+        assert (qk.float() - ref[:Mq, :768]).abs().max().item() < 2e-2
+        v_ref = ref[:Mq, 768:].view(Mq // tokens, tokens, 384).permute(0, 2, 1)
+        assert (vt.view(Mq // tokens, 384, 128)[:, :, :tokens].float() - v_ref).abs().max().item() < 2e-2
+
+
 def test_gemm_rejects_bad_shapes():
     from vittf_b200 import _lib, ops
     a, w, b = _mk(64, 100, 64)

@@ -1,7 +1,8 @@
 import sys, torch
 sys.path.insert(0, '.')
 from vittf_b200 import ops
-B, tokens, heads = 8, 4097, 6
+import os
+B, tokens, heads = int(os.environ.get('B', 8)), 4097, 6
 D = heads * 64
 qk = torch.randn(B * tokens, 2 * D, device="cuda").bfloat16()
 vt = torch.randn(B * D, ops.tok_pad_of(tokens), device="cuda").bfloat16()
@@ -15,4 +16,5 @@ for _ in range(10):
     a.record(); ops.attention(qk, vt, B, tokens, heads, ops.tok_pad_of(tokens)); b.record(); torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 import os
-print(os.environ.get("VITTF_LIB", "default"), "median ms", sorted(ts)[5])
+med = sorted(ts)[5]
+print(os.environ.get("VITTF_LIB", "default"), f"B={B} median ms {med:.4f}  {4.0 * B * heads * tokens * tokens * 64 / med / 1e9:.0f} TF/s")

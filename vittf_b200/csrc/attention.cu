@@ -4,8 +4,9 @@
 //
 // B200 design (one CTA per 256 query rows of one (image, head), 384 threads):
 //   warp 0    : TMA producer -- Q tiles once, then a 3-stage ring of K (128x64) and V^T (64x128) tiles
-//   warp 1    : MMA issuer   -- S = Q K^T (tcgen05.mma SS, 128x128x16, fp32 in TMEM), O += P V (tcgen05.mma TS:
-//                               P is read straight from TMEM, V^T from smem), for two query tiles.
+//   warp 1, 3 : MMA issuers, one per query tile -- S = Q K^T (tcgen05.mma SS, 128x128x16, fp32 in TMEM), O += P V
+//               (tcgen05.mma TS: P is read straight from TMEM, V^T from smem).  One issuing thread for both tiles
+//               was itself the critical path (clock64 traces: ~100 cycles per MMA of uniform-datapath bookkeeping).
 //   warp 2    : TMEM allocator (S_A, S_B: 2 x 128 cols; P_A, P_B: 2 x 64 cols; O_A, O_B: 2 x 64 cols = all 512).
 //               P has its own columns, so a softmax warp hands its S buffer back as soon as the scores are in
 //               registers and the MMA warp computes S(j+1) while the exponentials of block j are still running.
@@ -18,6 +19,8 @@
 //     exponential section through named barriers (ping-pong); left alone they drift into lock-step;
 //   * a quarter of the exponentials run as a Cody-Waite + cubic polynomial on the FMA pipe;
 //   * everything else is packed / 3-input instructions (FFMA2, FADD2, FMNMX3) with short dependency chains;
+//   * the last key block (tokens = 4097 = 32 * 128 + 1) is a 128x16 MMA and the only masked code path; the 32 full
+//     blocks carry no masking instructions (the predicated selects used to be 35 % of the loop);
 //   * roles are dispatched per warp with elect.sync so that ptxas keeps TMA/MMA descriptors in uniform registers
 //     (a branch on threadIdx.x cost ~75 cycles per MMA in divergence loops).
 #include <stdlib.h>
@@ -104,7 +107,18 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
 #ifndef HANDOVER_CH
 #define HANDOVER_CH 2      // hand the pipe over after 3 of the 4 column chunks
 #endif
-constexpr int POLY_EVERY = POLY_EVERY_V;   // every POLY_EVERY-th pair of exponentials runs on the FMA pipe (0 = none)
+#ifndef POLY_NUM
+#define POLY_NUM 1         // POLY_NUM of every POLY_EVERY_V pairs of exponentials run on the FMA pipe (0 = none)
+#endif
+#ifndef PINGPONG_V
+#define PINGPONG_V 1
+#endif
+constexpr bool PINGPONG = PINGPONG_V != 0;
+// pair index -> polynomial (FMA pipe) or MUFU; the polynomial pairs are spread evenly through the row
+__device__ __forceinline__ constexpr bool poly_slot(int pair) {
+    const int r = pair % POLY_EVERY_V;
+    return POLY_NUM > 0 && (r + 1) * POLY_NUM / POLY_EVERY_V != r * POLY_NUM / POLY_EVERY_V;
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, AttnParams p) {
@@ -120,8 +134,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     uint64_t* s_free = s_full + 2;            // [2] all 128 rows of S are in registers
     uint64_t* p_ready = s_free + 2;           // [2] P written
     uint64_t* pv_done = p_ready + 2;          // [2] P V finished (P buffer reusable, O stable)
-    uint64_t* o_final = pv_done + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
     const int lane = threadIdx.x & 31;
@@ -129,13 +142,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     const int q0 = unit * 2 * BQ;
     const bool has_b = q0 + BQ < p.tokens;
     const int n_tiles = has_b ? 2 : 1;
-    const int nkv = (p.tokens + BKV - 1) / BKV;
+    // keys: nfull blocks of 128 + one tail block that is only as wide as it has to be (tokens = 4097 = 32 * 128 + 1
+    // at 512^2 input: the tail costs a 128x16 MMA instead of a 33rd full block)
+    const int nfull = p.tokens / BKV;
+    const int tail = p.tokens - nfull * BKV;         // valid keys in the tail block (0 = none)
+    const int tail_n = (tail + 15) & ~15;            // its MMA N (scores) / K (P V) extent
+    const int nkv = nfull + (tail > 0 ? 1 : 0);
 
     if (threadIdx.x == 0) {   // one-time setup, not on the hot path
         ptx::mbar_init(q_full, 1);
         for (int i = 0; i < KV_STAGES; ++i) {
             ptx::mbar_init(&kv_full[i], 1);
-            ptx::mbar_init(&kv_empty[i], 1);
+            ptx::mbar_init(&kv_empty[i], n_tiles);   // one tcgen05.commit per query tile
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s_full[i], 1);
@@ -143,7 +161,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             ptx::mbar_init(&p_ready[i], 128);
             ptx::mbar_init(&pv_done[i], 1);
         }
-        ptx::mbar_init(o_final, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -181,58 +198,64 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                 ptx::tma_load_2d(dst + K_TILE_BYTES + V_HALF_BYTES, &tm_vt, &kv_full[st], j * BKV + 64, vt_row);
             }
         }
-      } else if (warp == 1 && ptx::elect_one()) {
-        // ---------------- MMA issuer ----------------
-        constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(BQ, BKV);
-        constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, HD);
-        const uint32_t q_addr = ptx::smem_u32(s_q);
-        const uint32_t kv_addr = ptx::smem_u32(s_kv);
-        auto issue_s = [&](int t, int st) {
-            const uint64_t adesc = ptx::smem_desc_k_sw128(q_addr + t * Q_TILE_BYTES);
-            const uint64_t bdesc = ptx::smem_desc_k_sw128(kv_addr + st * KV_STAGE_BYTES);
+      } else if ((warp == 1 || warp == 3) && ptx::elect_one()) {
+        // ---------------- MMA issuers: warp 1 drives query tile A, warp 3 tile B ----------------
+        // One thread per tile keeps the two tiles decoupled (an in-order issuer blocked on tile B's barrier cannot
+        // delay tile A) and its instruction stream short: the clock64 traces showed the single issuing thread, not
+        // the tensor pipe, on the critical path (~250 dependent uniform-datapath instructions per key block).
+        const int t = warp >> 1;
+        if (t < n_tiles) {
+            constexpr uint32_t idesc_s_full = ptx::idesc_bf16_f32(BQ, BKV);
+            const uint32_t idesc_s_tail = ptx::idesc_bf16_f32(BQ, tail_n);
+            constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, HD);
+            constexpr uint32_t STAGE_DESC = KV_STAGE_BYTES >> 4;    // descriptor address units are 16 B
+            constexpr uint32_t V_DESC = K_TILE_BYTES >> 4, VH_DESC = V_HALF_BYTES >> 4;
+            const uint32_t d_s = tmem_base + COL_S + t * 128, d_o = tmem_base + COL_O + t * 64, a_p = tmem_base + COL_P + t * 64;
+            const uint64_t q_desc = ptx::smem_desc_k_sw128(ptx::smem_u32(s_q) + t * Q_TILE_BYTES);
+            const uint64_t kv_desc0 = ptx::smem_desc_k_sw128(ptx::smem_u32(s_kv));
+            auto issue_s = [&](uint64_t k_desc, uint32_t idesc) {
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k)
-                ptx::umma_ss(tmem_base + COL_S + t * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-        };
-        auto issue_pv = [&](int t, int st, bool acc) {
-            const uint32_t v_addr = kv_addr + st * KV_STAGE_BYTES + K_TILE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < BKV / 16; ++ks) {
-                const uint64_t bdesc = ptx::smem_desc_k_sw128(v_addr + (ks >> 2) * V_HALF_BYTES) + 2 * (ks & 3);
-                // P: packed bf16 pairs, 8 TMEM columns per 16 keys
-                ptx::umma_ts(tmem_base + COL_O + t * 64, tmem_base + COL_P + t * 64 + ks * 8, bdesc, idesc_o,
-                             acc || ks != 0);
-            }
-        };
-        ptx::mbar_wait(q_full, 0);
-        ptx::mbar_wait(&kv_full[0], 0);
-        ptx::tc_fence_after();
-        for (int t = 0; t < n_tiles; ++t) {
-            issue_s(t, 0);
+                for (int k = 0; k < HD / 16; ++k) ptx::umma_ss(d_s, q_desc + 2 * k, k_desc + 2 * k, idesc, k != 0);
+            };
+            ptx::mbar_wait(q_full, 0);
+            ptx::mbar_wait(&kv_full[0], 0);
+            ptx::tc_fence_after();
+            issue_s(kv_desc0, nfull > 0 ? idesc_s_full : idesc_s_tail);
             ptx::tc_commit(&s_full[t]);
-        }
-        for (int j = 0; j < nkv; ++j) {
-            const int st = j % KV_STAGES;
-            if (j + 1 < nkv) {
-                ptx::mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
-                for (int t = 0; t < n_tiles; ++t) {   // S(j+1) as soon as block j's scores sit in registers
-                    TRACE(2, j, t * 2);
+            int st = 0;                      // ring stage of key block j
+            uint32_t ring_phase = 0;         // parity of kv_full for stage st
+            for (int j = 0; j < nkv; ++j) {
+                const int st1 = st + 1 == KV_STAGES ? 0 : st + 1;
+                const uint32_t phase1 = st1 == 0 ? ring_phase ^ 1 : ring_phase;
+                if (j + 1 < nkv) {           // S(j+1) as soon as block j's scores sit in registers
+                    ptx::mbar_wait(&kv_full[st1], phase1);
+                    if (t == 0) TRACE(2, j, 0);
                     ptx::mbar_wait(&s_free[t], j & 1);
                     ptx::tc_fence_after();
-                    issue_s(t, (j + 1) % KV_STAGES);
+                    issue_s(kv_desc0 + st1 * STAGE_DESC, j + 1 < nfull ? idesc_s_full : idesc_s_tail);
                     ptx::tc_commit(&s_full[t]);
+                    if (t == 0) TRACE(2, j, 1);
                 }
-            }
-            for (int t = 0; t < n_tiles; ++t) {
                 ptx::mbar_wait(&p_ready[t], j & 1);
-                TRACE(2, j, t * 2 + 1);
+                if (t == 0) TRACE(2, j, 2);
                 ptx::tc_fence_after();
-                issue_pv(t, st, j > 0);
+                const uint64_t v_desc = kv_desc0 + st * STAGE_DESC + V_DESC;
+                if (j < nfull) {
+                    // P: packed bf16 pairs, 8 TMEM columns per 16 keys; V^T: two 64-key halves
+#pragma unroll
+                    for (int ks = 0; ks < BKV / 16; ++ks)
+                        ptx::umma_ts(d_o, a_p + ks * 8, v_desc + (ks >> 2) * VH_DESC + 2 * (ks & 3), idesc_o, (j | ks) != 0);
+                } else {
+                    for (int ks = 0; ks < tail_n / 16; ++ks)
+                        ptx::umma_ts(d_o, a_p + ks * 8, v_desc + (ks >> 2) * VH_DESC + 2 * (ks & 3), idesc_o, (j | ks) != 0);
+                }
                 ptx::tc_commit(&pv_done[t]);
+                ptx::tc_commit(&kv_empty[st]);     // this tile is done with the stage (the barrier counts both tiles)
+                if (t == 0) TRACE(2, j, 3);
+                st = st1;
+                ring_phase = phase1;
             }
-            ptx::tc_commit(&kv_empty[st]);
         }
-        ptx::tc_commit(o_final);
       }
     } else {
         ptx::setmaxnreg_inc<216>();
@@ -251,38 +274,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             // Left alone they run their exponentials at the same time (pipe oversubscribed) and their TMEM loads /
             // row maxima at the same time (pipe idle); strict alternation keeps the pipe busy.
             const int bar_mine = 1 + q * 2 + t, bar_other = 1 + q * 2 + (t ^ 1);
-            if (has_b && t == 1) named_arrive(bar_other, 64);   // tile A goes first
-            for (int j = 0; j < nkv; ++j) {
-                if (q == 0 && lane == 0) TRACE(t, j, 0);
-                ptx::mbar_wait(&s_full[t], j & 1);
-                if (q == 0 && lane == 0) TRACE(t, j, 1);
-                ptx::tc_fence_after();
-                uint32_t s[4][32];
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(t_s + ch * 32, s[ch]);
-                ptx::tc_wait_ld();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(&s_free[t]);          // the MMA warp may overwrite S with the next block's scores
-                const int valid = p.tokens - j * BKV;  // >= 1
-                if (valid < BKV) {
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (ch * 32 + i >= valid) s[ch][i] = 0xff800000u;  // -inf
-                }
-                // row max: 8 independent chains of 3-input max
-                float mx[8];
-#pragma unroll
-                for (int a = 0; a < 8; ++a) mx[a] = __uint_as_float(s[a >> 1][(a & 1) * 16]);
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const uint32_t* sv = &s[a >> 1][(a & 1) * 16];
-#pragma unroll
-                    for (int i = 1; i < 15; i += 2) mx[a] = max3(mx[a], __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
-                    mx[a] = fmaxf(mx[a], __uint_as_float(sv[15]));
-                }
-                const float m_blk = max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * c;
+            if (PINGPONG && has_b && t == 1) named_arrive(bar_other, 64);   // tile A goes first
+            // lazy running-max update: O and l are rescaled only when the row max grew by more than 2^8
+            auto raise_max = [&](float m_blk, int j) {
                 const bool grow = m_blk > m_used + RESCALE_THRESHOLD;
                 if (__any_sync(0xffffffffu, grow)) {
                     const float m_new = grow ? m_blk : m_used;
@@ -303,8 +297,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     l *= f;
                     m_used = m_new;
                 }
+            };
+            // ---- full 128-key blocks: no masking anywhere on this path ----
+            for (int j = 0; j < nfull; ++j) {
+                if (q == 0 && lane == 0) TRACE(t, j, 0);
+                ptx::mbar_wait(&s_full[t], j & 1);
+                if (q == 0 && lane == 0) TRACE(t, j, 1);
+                ptx::tc_fence_after();
+                uint32_t s[4][32];
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(t_s + ch * 32, s[ch]);
+                ptx::tc_wait_ld();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&s_free[t]);          // the MMA warp may overwrite S with the next block's scores
+                // row max: 8 independent chains of 3-input max
+                float mx[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) mx[a] = __uint_as_float(s[a >> 1][(a & 1) * 16]);
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const uint32_t* sv = &s[a >> 1][(a & 1) * 16];
+#pragma unroll
+                    for (int i = 1; i < 15; i += 2) mx[a] = max3(mx[a], __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+                    mx[a] = fmaxf(mx[a], __uint_as_float(sv[15]));
+                }
+                raise_max(max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * c, j);
                 if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);   // P buffer free again (normally long since)
-                if (has_b) named_sync(bar_mine, 64);             // my turn on the exponential pipe
+                if (PINGPONG && has_b) named_sync(bar_mine, 64);       // my turn on the exponential pipe
                 if (q == 0 && lane == 0) TRACE(t, j, 2);
                 const float nm = -m_used;
                 ptx::F2 sums[4] = {{0ull}, {0ull}, {0ull}, {0ull}};    // 4 independent packed (2 x fp32) row-sum chains
@@ -316,7 +335,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                         float x0, x1;
                         ffma2(x0, x1, __uint_as_float(s[ch][2 * i]), __uint_as_float(s[ch][2 * i + 1]), c, nm);
                         float p0, p1;
-                        if (POLY_EVERY > 0 && (i % POLY_EVERY) == POLY_EVERY - 1) {
+                        if (poly_slot(ch * 16 + i)) {
                             exp2_poly2(x0, x1, p0, p1);
                         } else {
                             p0 = ptx::ex2_approx(x0);
@@ -327,7 +346,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     }
                     ptx::tmem_st16(t_p + ch * 16, pk);
                     // hand the exponential pipe to the other tile's warp a little before my last chunk drains
-                    if (ch == HANDOVER_CH && has_b && !(t == 1 && j == nkv - 1)) named_arrive(bar_other, 64);
+                    if (PINGPONG && ch == HANDOVER_CH && has_b && !(t == 1 && j == nkv - 1)) named_arrive(bar_other, 64);
                 }
                 {
                     float a0, a1, b0, b1;
@@ -340,8 +359,46 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&p_ready[t]);
             }
+            // ---- tail block: tail (< 128) valid keys in tail_n = ceil16(tail) score columns; the only masked path ----
+            if (tail > 0) {
+                const int j = nfull;
+                ptx::mbar_wait(&s_full[t], j & 1);
+                ptx::tc_fence_after();
+                float mx = -INFINITY;
+                for (int c0 = 0; c0 < tail_n; c0 += 16) {
+                    uint32_t v[16];
+                    ptx::tmem_ld16(t_s + c0, v);
+                    ptx::tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < tail) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
+                raise_max(mx * c, j);
+                if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);
+                if (PINGPONG && has_b) named_sync(bar_mine, 64);
+                const float nm = -m_used;
+                float sum = 0.0f;
+                for (int c0 = 0; c0 < tail_n; c0 += 16) {
+                    uint32_t v[16], pk[8];
+                    ptx::tmem_ld16(t_s + c0, v);
+                    ptx::tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float p0 = c0 + 2 * i < tail ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i]), c, nm)) : 0.0f;
+                        const float p1 = c0 + 2 * i + 1 < tail ? ptx::ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c, nm)) : 0.0f;
+                        sum += p0 + p1;
+                        pk[i] = ptx::pack_bf16x2(p0, p1);
+                    }
+                    ptx::tmem_st8(t_p + (c0 >> 1), pk);
+                }
+                l += sum;
+                if (PINGPONG && has_b && t == 0) named_arrive(bar_other, 64);   // tile B's tail block; nobody follows B
+                ptx::tc_wait_st();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&p_ready[t]);
+            }
             // ---- output: O / l -> bf16, token-major (B*tokens, D) at column head*64 ----
-            ptx::mbar_wait(o_final, 0);
+            ptx::mbar_wait(&pv_done[t], (nkv - 1) & 1);   // the last P V has landed in O
             ptx::tc_fence_after();
             const int row = q0 + t * BQ + q * 32 + lane;
             const float inv = 1.0f / l;

@@ -254,6 +254,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
@@ -274,7 +280,11 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
+#ifdef EX2_VOLATILE
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+#else
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+#endif
     return y;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
