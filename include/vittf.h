@@ -198,6 +198,26 @@ int64_t vittf_bls_workspace_bytes(const vittf_bls_params* p, int nrhs);
 int vittf_bls_solve(const vittf_bls_params* p, const float* t, const uint8_t* r_u8, const float* conf,
                     const int* luma_lut, int nrhs, float* out, int* iters_out, void* workspace,
                     int64_t workspace_bytes, void* stream);
+/* ---- the same solver in stages, for z-slab sharding over several GPUs ----
+ * Per-voxel arrays are slab-local (.., W, H, z1-z0); r_u8 is always the full (W,H,D) reference.
+ *   rank-local : vittf_bls_sobel_slab  -> raw Sobel magnitude of the slab, atomic max into *c_max
+ *   exchange   : all-reduce(max) of c_max                       (skipped when a confidence is given)
+ *   rank-local : vittf_bls_splat_slab  -> acc += [m | wbar | b_0..b_{nrhs-1}], (2+nrhs)*ncell fp64
+ *   exchange   : all-reduce(sum) of acc
+ *   replicated : vittf_bls_grid_solve  -> y (nrhs*ncell fp64): bistochastisation + PCG on the grid
+ *   rank-local : vittf_bls_slice_slab  -> out fp32 slab
+ * vittf_bls_solve is exactly this sequence with one slab.                                          */
+int64_t vittf_bls_grid_cells(const vittf_bls_params* p);
+int64_t vittf_bls_grid_workspace_bytes(const vittf_bls_params* p, int nrhs);
+int vittf_bls_sobel_slab(const uint8_t* r_u8, int W, int H, int D, int z0, int z1, float* c_raw_slab, float* c_max,
+                         void* stream);
+/* conf_slab: the confidence itself (c_max == NULL) or the raw Sobel magnitude with the global maximum in *c_max */
+int vittf_bls_splat_slab(const vittf_bls_params* p, const float* t_slab, const uint8_t* r_u8, const float* conf_slab,
+                         const float* c_max, const int* luma_lut, int nrhs, int z0, int z1, double* acc, void* stream);
+int vittf_bls_grid_solve(const vittf_bls_params* p, int nrhs, const double* acc, double* y, int* iters_out,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+int vittf_bls_slice_slab(const vittf_bls_params* p, const uint8_t* r_u8, const int* luma_lut, const double* y, int nrhs,
+                         int z0, int z1, float* out_slab, void* stream);
 /* Sobel confidence alone: out fp32 (W,H,D) = max(c) - c (needs a float scratch of 1 elem) */
 int vittf_sobel_confidence(const uint8_t* r_u8, int W, int H, int D, float* out, float* scratch_max, void* stream);
 

@@ -70,3 +70,50 @@ def test_crop_helpers(golden):
     assert torch.equal(crops[0], torch.from_numpy(g["c0"]))
     full = write_crop_into(torch.zeros_like(s), crops[0], (lo, hi))
     assert torch.equal(full[..., lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]], crops[0])
+
+
+def test_slab_sharded_solver_equals_single_pass():
+    """two ranks' z-slabs splatted into the same grid vectors (what the all-reduce(sum) produces) and
+    sliced per slab must reproduce the one-pass solve (fp64 atomics reorder the sums: 1e-6)."""
+    import ctypes as C
+    from vittf_b200 import _lib, ops, synth
+    from vittf_b200.bilateral_solver3d import luma_lut, solve_many
+    dev = torch.device("cuda")
+    r8, lab = synth.ct_volume((40, 36, 44), n_shells=4, seed=5)
+    t = torch.stack([(lab == c).float() * 0.8 + 0.1 + 0.05 * torch.rand(lab.shape) for c in range(3)]).to(dev)
+    r8 = r8.to(dev)
+    gp = dict(sigma_spatial=7, sigma_luma=5, sigma_chroma=5)
+    for conf in (None, torch.rand(40, 36, 44, device=dev)):
+        ref, it_ref = solve_many(t, r8, conf, gp)
+        # emulate world_size = 2 on one device: the "all-reduce" adds the other rank's partial grid vectors
+        lut = luma_lut(5)
+        lut_dev = torch.from_numpy(lut).to(dev)
+        slabs = [(0, 19), (19, 44)]
+        lib = _lib.load()
+        prm = _lib.BlsParams(40, 36, 44, 7.0, 256.0, 1e-5, 1e-5, 25, int(lut.max()) + 1)
+        ncell = lib.vittf_bls_grid_cells(C.byref(prm))
+        st = _lib.stream_ptr(dev)
+        cmax = torch.zeros(1, device=dev)
+        raws = []
+        if conf is None:
+            for z0, z1 in slabs:
+                raw = torch.empty(40, 36, z1 - z0, device=dev)
+                _lib.check(lib.vittf_bls_sobel_slab(_lib.ptr(r8), 40, 36, 44, z0, z1, _lib.ptr(raw), _lib.ptr(cmax), st), "sobel")
+                raws.append(raw)
+        acc = torch.zeros((2 + 3) * ncell, dtype=torch.float64, device=dev)
+        for k, (z0, z1) in enumerate(slabs):
+            ts = t[..., z0:z1].contiguous()
+            cs = raws[k] if conf is None else conf[..., z0:z1].contiguous()
+            _lib.check(lib.vittf_bls_splat_slab(C.byref(prm), _lib.ptr(ts), _lib.ptr(r8), _lib.ptr(cs),
+                                                _lib.ptr(cmax) if conf is None else None, _lib.ptr(lut_dev), 3, z0, z1,
+                                                _lib.ptr(acc), st), "splat")
+        outs = []
+        for z0, z1 in slabs:
+            # every rank solves the (identical) reduced grid problem and slices its own slab
+            o, it = ops.bls_solve_sharded(t[..., z0:z1].contiguous(), r8, None if conf is None else conf[..., z0:z1].contiguous(),
+                                          lut_dev, 7, 256, 1e-5, 1e-5, 25, int(lut.max()) + 1, z0, z1,
+                                          all_reduce_max=lambda x: x.copy_(cmax), all_reduce_sum=lambda x: x.copy_(acc))
+            outs.append(o)
+            assert torch.equal(it.cpu(), it_ref.cpu())
+        got = torch.cat(outs, dim=-1)
+        assert (got - ref).abs().max().item() < 1e-6

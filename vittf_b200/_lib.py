@@ -66,6 +66,12 @@ _SIGNATURES = {
     "vittf_bls_workspace_bytes": (_i64, [C.POINTER(BlsParams), _i]),
     "vittf_bls_solve": (_i, [C.POINTER(BlsParams), _p, _p, _p, _p, _i, _p, _p, _p, _i64, _p]),
     "vittf_sobel_confidence": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "vittf_bls_grid_cells": (_i64, [C.POINTER(BlsParams)]),
+    "vittf_bls_grid_workspace_bytes": (_i64, [C.POINTER(BlsParams), _i]),
+    "vittf_bls_sobel_slab": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "vittf_bls_splat_slab": (_i, [C.POINTER(BlsParams), _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "vittf_bls_grid_solve": (_i, [C.POINTER(BlsParams), _i, _p, _p, _p, _p, _i64, _p]),
+    "vittf_bls_slice_slab": (_i, [C.POINTER(BlsParams), _p, _p, _p, _i, _i, _i, _p, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -41,6 +41,27 @@ def solve_many(t, r0_u8, c=None, grid_params={}, bs_params={}):
                          gp['sigma_spatial'], bs['lam'], bs['A_diag_min'], bs['cg_tol'], bs['cg_maxiter'], int(lut.max()) + 1)
 
 
+def solve_many_sharded(t_slab, r0_u8, z_range, c_slab=None, grid_params={}, bs_params={}, group=None):
+    """Multi-GPU form of `solve_many`: this rank holds the z-slab `z_range` of the targets
+    (n,W,H,z1-z0) and of the optional confidence, and the full grey reference (W,H,D).  Pixel passes (Sobel, splat,
+    slice) are rank-local; ONE all-reduce(max) of the Sobel maximum and ONE all-reduce(sum) of the splatted grid
+    vectors (NCCL via torch.distributed) replace the halo exchange; the small grid problem is solved replicated.
+    Returns (fp32 slab (n,W,H,z1-z0) CUDA, iters)."""
+    import torch.distributed as dist
+    gp = {**grid_params_default, **grid_params}
+    bs = {**bs_params_default, **bs_params}
+    lut = luma_lut(gp['sigma_luma'])
+    lut_dev = torch.from_numpy(lut).to(t_slab.device)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    red_max = (lambda x: dist.all_reduce(x, op=dist.ReduceOp.MAX, group=group)) if multi else None
+    red_sum = (lambda x: dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)) if multi else None
+    z0, z1 = z_range
+    return ops.bls_solve_sharded(t_slab.float().contiguous(), r0_u8.contiguous(),
+                                 None if c_slab is None else c_slab.float().contiguous(), lut_dev, gp['sigma_spatial'],
+                                 bs['lam'], bs['A_diag_min'], bs['cg_tol'], bs['cg_maxiter'], int(lut.max()) + 1, z0, z1,
+                                 red_max, red_sum)
+
+
 def apply_bilateral_solver3d(t, r, c=None, grid_params={}, bs_params={}):
     """bilateral_solver3d.py:211-245.  t (1,W,H,D) float in [0,1], r (3,W,H,D) uint8, c optional
     (1,W,H,D) -> float32 (W,H,D) on the CPU (like the reference)."""

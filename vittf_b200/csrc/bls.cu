@@ -40,13 +40,15 @@ __device__ __forceinline__ int64_t cell_of(const Grid& g, int x, int y, int z, i
 }
 
 // ---- Sobel confidence (:176-181): fp32 central differences, zero padding, on r/255 -------------------
-__global__ void __launch_bounds__(256) sobel_kernel(const uint8_t* __restrict__ r, int W, int H, int D,
+// The volume may be processed in z-slabs [z0, z0+zs) (multi-GPU): r is always the FULL reference volume, the
+// per-voxel arrays (c, t, out) are slab-local (W, H, zs).
+__global__ void __launch_bounds__(256) sobel_kernel(const uint8_t* __restrict__ r, int W, int H, int D, int z0, int zs,
                                                     float* __restrict__ c_raw, float* __restrict__ c_max) {
-    const int64_t n = static_cast<int64_t>(W) * H * D;
+    const int64_t n = static_cast<int64_t>(W) * H * zs;
     float local = 0.0f;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int z = static_cast<int>(i % D), y = static_cast<int>((i / D) % H), x = static_cast<int>(i / (static_cast<int64_t>(D) * H));
+        const int z = z0 + static_cast<int>(i % zs), y = static_cast<int>((i / zs) % H), x = static_cast<int>(i / (static_cast<int64_t>(zs) * H));
         auto at = [&](int xx, int yy, int zz) -> float {
             if (xx < 0 || xx >= W || yy < 0 || yy >= H || zz < 0 || zz >= D) return 0.0f;
             return static_cast<float>(__ldg(r + (static_cast<int64_t>(xx) * H + yy) * D + zz)) / 255.0f;
@@ -72,19 +74,23 @@ __global__ void __launch_bounds__(256) confidence_finish_kernel(float* __restric
 }
 
 // ---- splat: m = S 1, wbar = S c, b_k = S (t_k * c) ----------------------------------------------------
-__global__ void __launch_bounds__(256) splat_kernel(Grid g, const uint8_t* __restrict__ r, const int* __restrict__ lut,
-                                                    const float* __restrict__ conf, const float* __restrict__ t, int nrhs,
+// conf is either the confidence itself (c_max == nullptr) or the raw Sobel magnitude, finished here as
+// c = max(c) - c (:237) with the GLOBAL maximum in *c_max.
+__global__ void __launch_bounds__(256) splat_kernel(Grid g, int z0, int zs, const uint8_t* __restrict__ r,
+                                                    const int* __restrict__ lut, const float* __restrict__ conf,
+                                                    const float* __restrict__ c_max, const float* __restrict__ t, int nrhs,
                                                     double* __restrict__ m, double* __restrict__ wbar,
                                                     double* __restrict__ b /* nrhs x ncell */) {
     __shared__ int s_lut[256];
     s_lut[threadIdx.x] = lut[threadIdx.x];
     __syncthreads();
-    const int64_t n = static_cast<int64_t>(g.W) * g.H * g.D;
+    const int64_t n = static_cast<int64_t>(g.W) * g.H * zs;
+    const float cm = c_max ? *c_max : 0.0f;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int z = static_cast<int>(i % g.D), y = static_cast<int>((i / g.D) % g.H), x = static_cast<int>(i / (static_cast<int64_t>(g.D) * g.H));
-        const int64_t cell = cell_of(g, x, y, z, s_lut[__ldg(r + i)]);
-        const double c = static_cast<double>(conf[i]);
+        const int z = z0 + static_cast<int>(i % zs), y = static_cast<int>((i / zs) % g.H), x = static_cast<int>(i / (static_cast<int64_t>(zs) * g.H));
+        const int64_t cell = cell_of(g, x, y, z, s_lut[__ldg(r + (static_cast<int64_t>(x) * g.H + y) * g.D + z)]);
+        const double c = static_cast<double>(c_max ? cm - conf[i] : conf[i]);
         atomicAdd(m + cell, 1.0);
         atomicAdd(wbar + cell, c);
         for (int k = 0; k < nrhs; ++k) atomicAdd(b + k * g.ncell + cell, static_cast<double>(t[k * n + i]) * c);
@@ -259,16 +265,17 @@ __global__ void __launch_bounds__(256) pcg_update_kernel(Grid g, const double* _
 }
 
 // ---- slice + float32 cast + nan_to_num (:153,245) -------------------------------------------------------
-__global__ void __launch_bounds__(256) slice_kernel(Grid g, const uint8_t* __restrict__ r, const int* __restrict__ lut,
-                                                    const double* __restrict__ y, int nrhs, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) slice_kernel(Grid g, int z0, int zs, const uint8_t* __restrict__ r,
+                                                    const int* __restrict__ lut, const double* __restrict__ y, int nrhs,
+                                                    float* __restrict__ out) {
     __shared__ int s_lut[256];
     s_lut[threadIdx.x] = lut[threadIdx.x];
     __syncthreads();
-    const int64_t n = static_cast<int64_t>(g.W) * g.H * g.D;
+    const int64_t n = static_cast<int64_t>(g.W) * g.H * zs;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int z = static_cast<int>(i % g.D), yy = static_cast<int>((i / g.D) % g.H), x = static_cast<int>(i / (static_cast<int64_t>(g.D) * g.H));
-        const int64_t cell = cell_of(g, x, yy, z, s_lut[__ldg(r + i)]);
+        const int z = z0 + static_cast<int>(i % zs), yy = static_cast<int>((i / zs) % g.H), x = static_cast<int>(i / (static_cast<int64_t>(zs) * g.H));
+        const int64_t cell = cell_of(g, x, yy, z, s_lut[__ldg(r + (static_cast<int64_t>(x) * g.H + yy) * g.D + z)]);
         for (int k = 0; k < nrhs; ++k) {
             float v = static_cast<float>(y[k * g.ncell + cell]);
             if (isnan(v)) v = 0.0f;
@@ -297,15 +304,48 @@ int make_grid(const vittf_bls_params* p, Grid* g) {
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+unsigned blocks_for(int64_t n) {
+    const int64_t bl = ceil_div_ll(n, 256), cap = static_cast<int64_t>(vittf_num_sms()) * 16;
+    return static_cast<unsigned>(bl < cap ? bl : cap);
+}
+int check_slab(const vittf_bls_params* p, int z0, int z1) {
+    VITTF_REQUIRE(z0 >= 0 && z1 > z0 && z1 <= p->D, "bls: bad z-slab [%d,%d) of depth %d", z0, z1, p->D);
+    return VITTF_OK;
+}
+
 }  // namespace
+
+extern "C" int64_t vittf_bls_grid_cells(const vittf_bls_params* p) {
+    Grid g;
+    if (!p || make_grid(p, &g) != VITTF_OK) return -1;
+    return g.ncell;
+}
+
+// scratch of the grid stage: m, n_a, n_b, minv (ncell each) + r, p, n*p, q (nrhs * ncell each) + scalars
+extern "C" int64_t vittf_bls_grid_workspace_bytes(const vittf_bls_params* p, int nrhs) {
+    Grid g;
+    if (!p || nrhs <= 0 || make_grid(p, &g) != VITTF_OK) return -1;
+    return 4 * align_up(g.ncell * 8, 256) + 4 * align_up(g.ncell * 8 * nrhs, 256) + align_up(nrhs * sizeof(RhsScalars), 256);
+}
 
 extern "C" int64_t vittf_bls_workspace_bytes(const vittf_bls_params* p, int nrhs) {
     Grid g;
     if (!p || nrhs <= 0 || make_grid(p, &g) != VITTF_OK) return -1;
-    const int64_t vec = align_up(g.ncell * 8, 256);
     const int64_t npix = static_cast<int64_t>(p->W) * p->H * p->D;
-    const int64_t per = align_up(g.ncell * 8 * nrhs, 256);   // per-rhs vectors are packed with stride ncell
-    return 6 * vec + 6 * per + align_up(npix * 4, 256) + align_up(nrhs * sizeof(RhsScalars), 256) + 256;
+    // acc (m_cnt | wbar | b) + y + grid scratch + Sobel magnitude + its maximum
+    return align_up((2 + nrhs) * g.ncell * 8, 256) + align_up(g.ncell * 8 * nrhs, 256) + vittf_bls_grid_workspace_bytes(p, nrhs) +
+           align_up(npix * 4, 256) + 256;
+}
+
+extern "C" int vittf_bls_sobel_slab(const uint8_t* r_u8, int W, int H, int D, int z0, int z1, float* c_raw_slab, float* c_max,
+                                    void* stream) {
+    VITTF_REQUIRE(r_u8 && c_raw_slab && c_max && W > 0 && H > 0 && D > 0 && z0 >= 0 && z1 > z0 && z1 <= D,
+                  "vittf_bls_sobel_slab: bad arguments");
+    const int64_t n = static_cast<int64_t>(W) * H * (z1 - z0);
+    sobel_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(r_u8, W, H, D, z0, z1 - z0, c_raw_slab, c_max);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
 }
 
 extern "C" int vittf_sobel_confidence(const uint8_t* r_u8, int W, int H, int D, float* out, float* scratch_max, void* stream) {
@@ -313,64 +353,58 @@ extern "C" int vittf_sobel_confidence(const uint8_t* r_u8, int W, int H, int D, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t n = static_cast<int64_t>(W) * H * D;
     VITTF_CHECK_CUDA(cudaMemsetAsync(scratch_max, 0, sizeof(float), s));
-    int64_t blocks = ceil_div_ll(n, 256);
-    const int64_t cap = static_cast<int64_t>(vittf_num_sms()) * 16;
-    if (blocks > cap) blocks = cap;
-    sobel_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(r_u8, W, H, D, out, scratch_max);
-    confidence_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(out, n, scratch_max);
+    VITTF_CHECK(vittf_bls_sobel_slab(r_u8, W, H, D, 0, D, out, scratch_max, stream));
+    confidence_finish_kernel<<<blocks_for(n), 256, 0, s>>>(out, n, scratch_max);
     VITTF_CHECK_CUDA(cudaGetLastError());
-    vittf_count_launches(2);
+    vittf_count_launches(1);
     return VITTF_OK;
 }
 
-extern "C" int vittf_bls_solve(const vittf_bls_params* p, const float* t, const uint8_t* r_u8, const float* conf,
-                               const int* luma_lut, int nrhs, float* out, int* iters_out, void* workspace,
-                               int64_t workspace_bytes, void* stream) {
-    VITTF_REQUIRE(p && t && r_u8 && luma_lut && out && workspace, "vittf_bls_solve: null pointer");
-    VITTF_REQUIRE(nrhs > 0 && nrhs <= 64, "vittf_bls_solve: nrhs must be in [1,64]");
+extern "C" int vittf_bls_splat_slab(const vittf_bls_params* p, const float* t_slab, const uint8_t* r_u8, const float* conf_slab,
+                                    const float* c_max, const int* luma_lut, int nrhs, int z0, int z1, double* acc,
+                                    void* stream) {
+    VITTF_REQUIRE(p && t_slab && r_u8 && conf_slab && luma_lut && acc, "vittf_bls_splat_slab: null pointer");
+    VITTF_REQUIRE(nrhs > 0 && nrhs <= 64, "vittf_bls_splat_slab: nrhs must be in [1,64]");
     Grid g;
     VITTF_CHECK(make_grid(p, &g));
-    const int64_t need = vittf_bls_workspace_bytes(p, nrhs);
+    VITTF_CHECK(check_slab(p, z0, z1));
+    const int64_t n = static_cast<int64_t>(g.W) * g.H * (z1 - z0);
+    splat_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, z0, z1 - z0, r_u8, luma_lut, conf_slab, c_max,
+                                                                               t_slab, nrhs, acc, acc + g.ncell, acc + 2 * g.ncell);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
+
+extern "C" int vittf_bls_grid_solve(const vittf_bls_params* p, int nrhs, const double* acc, double* y, int* iters_out,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
+    VITTF_REQUIRE(p && acc && y && workspace, "vittf_bls_grid_solve: null pointer");
+    VITTF_REQUIRE(nrhs > 0 && nrhs <= 64, "vittf_bls_grid_solve: nrhs must be in [1,64]");
+    Grid g;
+    VITTF_CHECK(make_grid(p, &g));
+    const int64_t need = vittf_bls_grid_workspace_bytes(p, nrhs);
     if (workspace_bytes < need) {
-        vittf_set_error("vittf_bls_solve: workspace of %lld B is smaller than the %lld B required", (long long)workspace_bytes, (long long)need);
+        vittf_set_error("vittf_bls_grid_solve: workspace of %lld B is smaller than the %lld B required", (long long)workspace_bytes, (long long)need);
         return VITTF_ERR_NOMEM;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int64_t vec = align_up(g.ncell * 8, 256);
-    const int64_t npix = static_cast<int64_t>(g.W) * g.H * g.D;
+    const int64_t vec = align_up(g.ncell * 8, 256), per = align_up(g.ncell * 8 * nrhs, 256);
     uint8_t* base = static_cast<uint8_t*>(workspace);
     auto take = [&](int64_t bytes) { uint8_t* r = base; base += bytes; return r; };
-    double* m_cnt = reinterpret_cast<double*>(take(vec));
+    const double* m_cnt = acc;
+    const double* wbar = acc + g.ncell;
+    const double* b = acc + 2 * g.ncell;
     double* m = reinterpret_cast<double*>(take(vec));
     double* n_a = reinterpret_cast<double*>(take(vec));
     double* n_b = reinterpret_cast<double*>(take(vec));
-    double* wbar = reinterpret_cast<double*>(take(vec));
     double* minv = reinterpret_cast<double*>(take(vec));
-    const int64_t per = align_up(g.ncell * 8 * nrhs, 256);
-    double* b = reinterpret_cast<double*>(take(per));
-    double* y = reinterpret_cast<double*>(take(per));
     double* r = reinterpret_cast<double*>(take(per));
     double* pd = reinterpret_cast<double*>(take(per));
     double* np = reinterpret_cast<double*>(take(per));
     double* q = reinterpret_cast<double*>(take(per));
-    float* c_buf = reinterpret_cast<float*>(take(align_up(npix * 4, 256)));
     RhsScalars* sc = reinterpret_cast<RhsScalars*>(take(align_up(nrhs * sizeof(RhsScalars), 256)));
-    float* c_max = reinterpret_cast<float*>(take(256));
-
-    const int sms = vittf_num_sms();
-    auto blocks_for = [&](int64_t n) { int64_t bl = ceil_div_ll(n, 256); int64_t cap = static_cast<int64_t>(sms) * 16; return static_cast<unsigned>(bl < cap ? bl : cap); };
-    const unsigned gp = blocks_for(npix), gc = blocks_for(g.ncell);
-
-    const float* cptr = conf;
-    if (!conf) {
-        VITTF_CHECK(vittf_sobel_confidence(r_u8, g.W, g.H, g.D, c_buf, c_max, stream));
-        cptr = c_buf;
-    }
-    VITTF_CHECK_CUDA(cudaMemsetAsync(m_cnt, 0, vec, s));
-    VITTF_CHECK_CUDA(cudaMemsetAsync(wbar, 0, vec, s));
-    VITTF_CHECK_CUDA(cudaMemsetAsync(b, 0, per, s));
+    const unsigned gc = blocks_for(g.ncell);
     VITTF_CHECK_CUDA(cudaMemsetAsync(sc, 0, nrhs * sizeof(RhsScalars), s));
-    splat_kernel<<<gp, 256, 0, s>>>(g, r_u8, luma_lut, cptr, t, nrhs, m_cnt, wbar, b);
     occ_init_kernel<<<gc, 256, 0, s>>>(g.ncell, m_cnt, n_a);
     double* n_cur = n_a;
     double* n_nxt = n_b;
@@ -388,9 +422,58 @@ extern "C" int vittf_bls_solve(const vittf_bls_params* p, const float* t, const 
         pcg_apply_kernel<<<gk, 256, 0, s>>>(g, m, n_cur, wbar, pd, np, p->lam, q, sc);
         pcg_update_kernel<<<gk, 256, 0, s>>>(g, minv, pd, q, y, r, sc);
     }
-    slice_kernel<<<gp, 256, 0, s>>>(g, r_u8, luma_lut, y, nrhs, out);
     if (iters_out) copy_iters_kernel<<<1, 64, 0, s>>>(sc, nrhs, iters_out);
     VITTF_CHECK_CUDA(cudaGetLastError());
-    vittf_count_launches(2 + 10 + 1 + 2 + 4 * p->cg_maxiter + 1 + (iters_out ? 1 : 0));
+    vittf_count_launches(10 + 1 + 1 + 2 + 4 * p->cg_maxiter + (iters_out ? 1 : 0));
+    return VITTF_OK;
+}
+
+extern "C" int vittf_bls_slice_slab(const vittf_bls_params* p, const uint8_t* r_u8, const int* luma_lut, const double* y, int nrhs,
+                                    int z0, int z1, float* out_slab, void* stream) {
+    VITTF_REQUIRE(p && r_u8 && luma_lut && y && out_slab && nrhs > 0, "vittf_bls_slice_slab: bad arguments");
+    Grid g;
+    VITTF_CHECK(make_grid(p, &g));
+    VITTF_CHECK(check_slab(p, z0, z1));
+    const int64_t n = static_cast<int64_t>(g.W) * g.H * (z1 - z0);
+    slice_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, z0, z1 - z0, r_u8, luma_lut, y, nrhs, out_slab);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
+
+// Single-GPU composition of the stages above (the whole volume is one slab).
+extern "C" int vittf_bls_solve(const vittf_bls_params* p, const float* t, const uint8_t* r_u8, const float* conf,
+                               const int* luma_lut, int nrhs, float* out, int* iters_out, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+    VITTF_REQUIRE(p && t && r_u8 && luma_lut && out && workspace, "vittf_bls_solve: null pointer");
+    VITTF_REQUIRE(nrhs > 0 && nrhs <= 64, "vittf_bls_solve: nrhs must be in [1,64]");
+    Grid g;
+    VITTF_CHECK(make_grid(p, &g));
+    const int64_t need = vittf_bls_workspace_bytes(p, nrhs);
+    if (workspace_bytes < need) {
+        vittf_set_error("vittf_bls_solve: workspace of %lld B is smaller than the %lld B required", (long long)workspace_bytes, (long long)need);
+        return VITTF_ERR_NOMEM;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t npix = static_cast<int64_t>(g.W) * g.H * g.D;
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    auto take = [&](int64_t bytes) { uint8_t* r = base; base += bytes; return r; };
+    const int64_t acc_bytes = align_up((2 + nrhs) * g.ncell * 8, 256);
+    double* acc = reinterpret_cast<double*>(take(acc_bytes));
+    double* y = reinterpret_cast<double*>(take(align_up(g.ncell * 8 * nrhs, 256)));
+    const int64_t grid_bytes = vittf_bls_grid_workspace_bytes(p, nrhs);
+    void* grid_ws = take(grid_bytes);
+    float* c_buf = reinterpret_cast<float*>(take(align_up(npix * 4, 256)));
+    float* c_max = reinterpret_cast<float*>(take(256));
+    VITTF_CHECK_CUDA(cudaMemsetAsync(acc, 0, acc_bytes, s));
+    if (!conf) {
+        VITTF_CHECK_CUDA(cudaMemsetAsync(c_max, 0, sizeof(float), s));
+        VITTF_CHECK(vittf_bls_sobel_slab(r_u8, g.W, g.H, g.D, 0, g.D, c_buf, c_max, stream));
+        VITTF_CHECK(vittf_bls_splat_slab(p, t, r_u8, c_buf, c_max, luma_lut, nrhs, 0, g.D, acc, stream));
+    } else {
+        VITTF_CHECK(vittf_bls_splat_slab(p, t, r_u8, conf, nullptr, luma_lut, nrhs, 0, g.D, acc, stream));
+    }
+    VITTF_CHECK(vittf_bls_grid_solve(p, nrhs, acc, y, iters_out, grid_ws, grid_bytes, stream));
+    VITTF_CHECK(vittf_bls_slice_slab(p, r_u8, luma_lut, y, nrhs, 0, g.D, out, stream));
     return VITTF_OK;
 }

@@ -185,3 +185,47 @@ def bls_solve(t, r_u8, conf, luma_lut, sigma_spatial, lam, diag_min, cg_tol, cg_
     check(load().vittf_bls_solve(C.byref(prm), ptr(t), ptr(r_u8), ptr(conf), ptr(luma_lut), nrhs, ptr(out), ptr(iters),
                                  ptr(ws), need, stream_ptr(t.device)), "vittf_bls_solve")
     return out, iters
+
+
+def bls_solve_sharded(t_slab, r_u8, conf_slab, luma_lut, sigma_spatial, lam, diag_min, cg_tol, cg_maxiter, luma_bins, z0, z1,
+                      all_reduce_max=None, all_reduce_sum=None):
+    """The solver in stages over the z-slab [z0, z1) of this rank: t_slab (nrhs,W,H,z1-z0) fp32,
+    r_u8 the FULL (W,H,D) reference, conf_slab (W,H,z1-z0) or None (Sobel).  `all_reduce_max(tensor)` /
+    `all_reduce_sum(tensor)` are the two exchanges (in place; None = single rank).  The grid stage (bistochastisation
+    + PCG) runs replicated.  Returns (out slab fp32 (nrhs,W,H,z1-z0), iters int32 (nrhs))."""
+    require_cuda(t_slab, r_u8, conf_slab, luma_lut)
+    nrhs = t_slab.shape[0]
+    W, H, D = r_u8.shape
+    zs = z1 - z0
+    if tuple(t_slab.shape[1:]) != (W, H, zs):
+        raise ValueError(f"t_slab must be (nrhs,{W},{H},{zs}), got {tuple(t_slab.shape)}")
+    dev = t_slab.device
+    prm = _lib.BlsParams(W, H, D, float(sigma_spatial), float(lam), float(diag_min), float(cg_tol), int(cg_maxiter),
+                         int(luma_bins))
+    lib = load()
+    ncell = lib.vittf_bls_grid_cells(C.byref(prm))
+    if ncell < 0:
+        raise _lib.VittfError("vittf_bls_grid_cells: bad parameters")
+    st = stream_ptr(dev)
+    acc = torch.zeros((2 + nrhs) * ncell, dtype=torch.float64, device=dev)
+    if conf_slab is None:
+        c_raw = torch.empty(W, H, zs, dtype=torch.float32, device=dev)
+        c_max = torch.zeros(1, dtype=torch.float32, device=dev)
+        check(lib.vittf_bls_sobel_slab(ptr(r_u8), W, H, D, z0, z1, ptr(c_raw), ptr(c_max), st), "vittf_bls_sobel_slab")
+        if all_reduce_max is not None:
+            all_reduce_max(c_max)
+        check(lib.vittf_bls_splat_slab(C.byref(prm), ptr(t_slab), ptr(r_u8), ptr(c_raw), ptr(c_max), ptr(luma_lut), nrhs, z0, z1,
+                                       ptr(acc), st), "vittf_bls_splat_slab")
+    else:
+        check(lib.vittf_bls_splat_slab(C.byref(prm), ptr(t_slab), ptr(r_u8), ptr(conf_slab), None, ptr(luma_lut), nrhs, z0, z1,
+                                       ptr(acc), st), "vittf_bls_splat_slab")
+    if all_reduce_sum is not None:
+        all_reduce_sum(acc)
+    y = torch.empty(nrhs * ncell, dtype=torch.float64, device=dev)
+    iters = torch.zeros(nrhs, dtype=torch.int32, device=dev)
+    need = lib.vittf_bls_grid_workspace_bytes(C.byref(prm), nrhs)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    check(lib.vittf_bls_grid_solve(C.byref(prm), nrhs, ptr(acc), ptr(y), ptr(iters), ptr(ws), need, st), "vittf_bls_grid_solve")
+    out = torch.empty(nrhs, W, H, zs, dtype=torch.float32, device=dev)
+    check(lib.vittf_bls_slice_slab(C.byref(prm), ptr(r_u8), ptr(luma_lut), ptr(y), nrhs, z0, z1, ptr(out), st), "vittf_bls_slice_slab")
+    return out, iters

@@ -7,6 +7,7 @@ import torch
 import torch.nn.functional as F
 
 from . import dist, infer, ops
+from .bilateral_solver3d import solve_many_sharded
 from .similarity import class_offsets, rel_coords, similarity_maps
 
 
@@ -32,3 +33,13 @@ def volume_to_similarity(vol_dev, model, annotations, patch=8, fos=64, batch_siz
     sims = similarity_maps(feats, protos, offs, out_shape, mode="ns", exponent=exponent, z_range=zr)
     labels = ops.labels(sims, None, mode=1) if want_labels else None
     return feats, sims, labels, zr
+
+
+def refine_similarity(sims_slab, ref_u8, z_range, grid_params=None, bs_params=None, group=None):
+    """bilateral_solver3d refinement of per-class maps (configs[4]): sims_slab fp32 (C,W,H,z1-z0) = this rank's
+    z-slab, ref_u8 the full grey uint8 volume (W,H,D) at the maps' resolution.  All classes share the reference and
+    are solved together; with several ranks the pixel passes are slab-local and the grid vectors are all-reduced
+    (bilateral_solver3d.solve_many_sharded).  Returns the refined slab fp32 (C,W,H,z1-z0)."""
+    gp = {'sigma_spatial': 7, 'sigma_chroma': 5, 'sigma_luma': 5} if grid_params is None else grid_params   # predict_ntf.py:75-79
+    out, _ = solve_many_sharded(sims_slab, ref_u8, z_range, None, gp, bs_params or {}, group=group)
+    return out
