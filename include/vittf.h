@@ -221,6 +221,13 @@ int vittf_bls_slice_slab(const vittf_bls_params* p, const uint8_t* r_u8, const i
 /* Sobel confidence alone: out fp32 (W,H,D) = max(c) - c (needs a float scratch of 1 elem) */
 int vittf_sobel_confidence(const uint8_t* r_u8, int W, int H, int D, float* out, float* scratch_max, void* stream);
 
+/* =====================================================================================
+ * Annotation samplers (compare_feat_sampling.py:13-33) -- SURVEY.md 8f row 1
+ * ===================================================================================== */
+/* scipy.ndimage.binary_erosion(mask, generate_binary_structure(3, connectivity)) with border_value 0:
+ * mask / out uint8 (W,H,D), non-zero = foreground; connectivity >= 3 is the full 3x3x3 box (:20-23). */
+int vittf_binary_erosion(const uint8_t* mask, int W, int H, int D, int connectivity, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,13 +54,38 @@ def reference_feature_volume(infer, vol, model, patch, fos, batch_size):
     return qkv["k"], im_sz
 
 
+def golden_sampling():
+    """compare_feat_sampling.py:13-33 under torch.manual_seed: index sets the drop-in must reproduce."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import synth
+    import_reference()
+    import compare_feat_sampling as cfs
+    lab = synth.shell_labels((30, 26, 22), 3)
+    out = {"shape": np.array(lab.shape)}
+    for cls in (0, 1, 2):
+        mask = (lab == cls).numpy()
+        torch.manual_seed(100 + cls)
+        out[f"uniform_{cls}"] = cfs.sample_uniform(mask, 12).numpy()
+        torch.manual_seed(200 + cls)
+        out[f"surface_{cls}"] = cfs.sample_surface(mask, 10, dist_from_surface=4).numpy()
+        torch.manual_seed(300 + cls)
+        out[f"both_{cls}"] = cfs.sample_both(mask, 16, dist_from_surface=4).numpy()
+        torch.manual_seed(400 + cls)
+        out[f"surface_all_{cls}"] = cfs.sample_surface(mask, 10 ** 6, dist_from_surface=2).numpy()   # "< n_samples" branch
+    np.savez_compressed(OUT / "sampling.npz", **out)
+    print("sampling", {k: v.shape for k, v in out.items()})
+
+
 def main():
     warnings.filterwarnings("ignore")
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "sampling":
+        return golden_sampling()
     sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
     from oracle import dino_vit, synth
     infer, predict_ntf, bls3d = import_reference()
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
+    golden_sampling()
 
     # ---------------------------------------------------------------- stage 1: feature volume
     cases = {

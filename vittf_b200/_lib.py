@@ -66,6 +66,7 @@ _SIGNATURES = {
     "vittf_bls_workspace_bytes": (_i64, [C.POINTER(BlsParams), _i]),
     "vittf_bls_solve": (_i, [C.POINTER(BlsParams), _p, _p, _p, _p, _i, _p, _p, _p, _i64, _p]),
     "vittf_sobel_confidence": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "vittf_binary_erosion": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "vittf_bls_grid_cells": (_i64, [C.POINTER(BlsParams)]),
     "vittf_bls_grid_workspace_bytes": (_i64, [C.POINTER(BlsParams), _i]),
     "vittf_bls_sobel_slab": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),

@@ -229,3 +229,16 @@ def bls_solve_sharded(t_slab, r_u8, conf_slab, luma_lut, sigma_spatial, lam, dia
     out = torch.empty(nrhs, W, H, zs, dtype=torch.float32, device=dev)
     check(lib.vittf_bls_slice_slab(C.byref(prm), ptr(r_u8), ptr(luma_lut), ptr(y), nrhs, z0, z1, ptr(out), st), "vittf_bls_slice_slab")
     return out, iters
+
+
+def binary_erosion(mask_u8, connectivity):
+    """scipy.ndimage.binary_erosion(mask, generate_binary_structure(3, connectivity)) (border_value 0) on the device:
+    mask uint8 (W,H,D) -> uint8 (W,H,D)."""
+    require_cuda(mask_u8)
+    if mask_u8.dtype != torch.uint8 or mask_u8.dim() != 3:
+        raise TypeError("binary_erosion expects a 3-D uint8 mask")
+    W, H, D = mask_u8.shape
+    out = torch.empty_like(mask_u8)
+    check(load().vittf_binary_erosion(ptr(mask_u8), W, H, D, int(connectivity), ptr(out), stream_ptr(mask_u8.device)),
+          "vittf_binary_erosion")
+    return out
