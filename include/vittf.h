@@ -157,7 +157,8 @@ int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w, int h, int
 typedef enum {
     VITTF_SIM_NS = 0,     /* interp(features) -> L2 normalise -> dot -> clamp(0,1)^e -> class MAX */
     VITTF_SIM_REFNTF = 1, /* raw dot -> where(>=thr)^e -> class MEAN           (predict_ntf.py:71-72) */
-    VITTF_SIM_LEGACY = 2  /* normalise at low res -> dot -> clamp(0,1)^e -> MAX (cluster_dino.py:307-322) */
+    VITTF_SIM_LEGACY = 2, /* normalise at low res -> dot -> clamp(0,1)^e -> MAX (cluster_dino.py:307-322) */
+    VITTF_SIM_CLAMP_MEAN = 3 /* raw dot -> clamp(0,1)^e -> group MEAN               (infer.py:104-106, resample_topk) */
 } vittf_sim_mode;
 
 /* Second pass: per OUTPUT voxel combine the 8 surrounding low-res dots (trilinear,
@@ -224,6 +225,11 @@ int vittf_sobel_confidence(const uint8_t* r_u8, int W, int H, int D, float* out,
 /* =====================================================================================
  * Annotation samplers (compare_feat_sampling.py:13-33) -- SURVEY.md 8f row 1
  * ===================================================================================== */
+/* resample_topk (infer.py:90-94), per similarity map (n_maps x n fp32): thr = K-th largest value, out_idx = the first K
+ * flat voxel indices in index order with value >= thr (the reference's `(s >= thr).nonzero()[:K]`); out_thr may be NULL. */
+int vittf_topk_voxels(const float* maps, int n_maps, int64_t n, int K, long long* out_idx, float* out_thr, void* stream);
+/* take_most_dissimilar (infer.py:118-121): out[i] = 1 - mean_j cos(f_i, f_j) (measure 0) or mean_j |f_i - f_j| (1) */
+int vittf_mean_pairwise_distance(const float* feats, int N, int F, int measure, float* out, void* stream);
 /* scipy.ndimage.binary_erosion(mask, generate_binary_structure(3, connectivity)) with border_value 0:
  * mask / out uint8 (W,H,D), non-zero = foreground; connectivity >= 3 is the full 3x3x3 box (:20-23). */
 int vittf_binary_erosion(const uint8_t* mask, int W, int H, int D, int connectivity, uint8_t* out, void* stream);

@@ -76,16 +76,42 @@ def golden_sampling():
     print("sampling", {k: v.shape for k, v in out.items()})
 
 
+def golden_refine():
+    """infer.py:75-126 (resample_topk, take_most_dissimilar) on a small class-structured feature volume."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import synth
+    infer, _, _ = import_reference()
+    lr = (12, 10, 8)
+    feats, protos = synth.class_features(32, lr, 3, seed=9, dtype=torch.float32)
+    g = torch.Generator().manual_seed(4)
+    p = torch.nn.functional.normalize(protos.repeat(2, 1) + 0.05 * torch.randn(6, 32, generator=g), dim=-1).view(3, 2, 32)
+    sims = (torch.einsum("fwhd,caf->cawhd", feats, p).clamp(0, 1) ** 2.0)
+    sims[0, 0] = (sims[0, 0] * 4).round() / 4                   # heavy ties: exercises the `nonzero()[:K]` rule
+    out = {"sims_in": sims.numpy()}
+    for K in (3, 8):
+        out[f"topk{K}"] = infer.resample_topk(feats.clone()[None], sims.clone(), K=K, similarity_exponent=2.0).numpy()[0]
+    f2 = torch.randn(40, 16, generator=g)
+    f2[:5] *= 3.0
+    for measure in ("cosine", "euclidean"):
+        out[f"dissim_{measure}"] = infer.take_most_dissimilar(f2.clone(), num_prototypes=9, measure=measure).numpy()
+    out["dissim_in"] = f2.numpy()
+    np.savez_compressed(OUT / "refine.npz", **out)
+    print("refine", {k: v.shape for k, v in out.items()})
+
+
 def main():
     warnings.filterwarnings("ignore")
     if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "sampling":
         return golden_sampling()
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "refine":
+        return golden_refine()
     sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
     from oracle import dino_vit, synth
     infer, predict_ntf, bls3d = import_reference()
     OUT.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
     golden_sampling()
+    golden_refine()
 
     # ---------------------------------------------------------------- stage 1: feature volume
     cases = {

@@ -36,7 +36,7 @@ class BlsParams(C.Structure):
 U8, F16, BF16, F32, F64 = 0, 1, 2, 3, 4
 DTYPE_CODE = {torch.uint8: U8, torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32, torch.float64: F64}
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_QKV_SPLIT, EPI_KFEAT_F16 = range(5)
-SIM_NS, SIM_REFNTF, SIM_LEGACY = 0, 1, 2
+SIM_NS, SIM_REFNTF, SIM_LEGACY, SIM_CLAMP_MEAN = 0, 1, 2, 3
 
 _p, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 _SIGNATURES = {
@@ -67,6 +67,8 @@ _SIGNATURES = {
     "vittf_bls_solve": (_i, [C.POINTER(BlsParams), _p, _p, _p, _p, _i, _p, _p, _p, _i64, _p]),
     "vittf_sobel_confidence": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "vittf_binary_erosion": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "vittf_topk_voxels": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
+    "vittf_mean_pairwise_distance": (_i, [_p, _i, _i, _i, _p, _p]),
     "vittf_bls_grid_cells": (_i64, [C.POINTER(BlsParams)]),
     "vittf_bls_grid_workspace_bytes": (_i64, [C.POINTER(BlsParams), _i]),
     "vittf_bls_sobel_slab": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),

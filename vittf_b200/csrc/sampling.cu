@@ -30,7 +30,127 @@ __global__ void __launch_bounds__(256) binary_erosion_kernel(const uint8_t* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// resample_topk (infer.py:90-94): per similarity map, thr = K-th largest value (with multiplicity), then the FIRST K
+// voxels in index order with s >= thr -- `(s >= thr).nonzero()[:K]`, which is not "the K largest" when thr is tied.
+// One CTA per map: K rounds of (value, lowest index) arg-max over not-yet-taken voxels, then an ordered scan.
+// ---------------------------------------------------------------------------------------------
+constexpr int TOPK_MAX = 64;
+
+__global__ void __launch_bounds__(512) topk_voxels_kernel(const float* __restrict__ maps, int64_t n, int K,
+                                                          long long* __restrict__ out_idx, float* __restrict__ out_thr) {
+    __shared__ float s_val[16];
+    __shared__ long long s_idx[16];
+    __shared__ long long s_taken[TOPK_MAX];
+    __shared__ float s_thr;
+    __shared__ int s_count[17];
+    const float* m = maps + static_cast<int64_t>(blockIdx.x) * n;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int round = 0; round < K; ++round) {
+        float bv = -INFINITY;
+        long long bi = -1;
+        for (int64_t i = tid; i < n; i += blockDim.x) {
+            const float v = m[i];
+            if (!(v > bv)) continue;                       // strict: the lowest index wins among equal values
+            bool taken = false;
+            for (int t = 0; t < round; ++t) taken = taken || s_taken[t] == i;
+            if (!taken) { bv = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[wid] = bv; s_idx[wid] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
+                if (s_idx[w] >= 0 && (s_idx[0] < 0 || s_val[w] > s_val[0] || (s_val[w] == s_val[0] && s_idx[w] < s_idx[0]))) {
+                    s_val[0] = s_val[w];
+                    s_idx[0] = s_idx[w];
+                }
+            s_taken[round] = s_idx[0];
+            s_thr = s_val[0];
+        }
+        __syncthreads();
+    }
+    const float thr = s_thr;
+    if (tid == 0 && out_thr) out_thr[blockIdx.x] = thr;
+    // ordered selection of the first K voxels with value >= thr: chunks of blockDim voxels, warp ballots for the ranks
+    int found = 0;
+    for (int64_t base = 0; base < n && found < K; base += blockDim.x) {
+        const int64_t i = base + tid;
+        const bool hit = i < n && m[i] >= thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_count[wid + 1] = __popc(bal);
+        __syncthreads();
+        if (tid == 0) {
+            s_count[0] = 0;
+            for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) s_count[w + 1] += s_count[w];
+        }
+        __syncthreads();
+        const int rank = found + s_count[wid] + __popc(bal & ((1u << lane) - 1u));
+        if (hit && rank < K) out_idx[static_cast<int64_t>(blockIdx.x) * K + rank] = i;
+        found += s_count[blockDim.x >> 5];
+        __syncthreads();
+    }
+}
+
+// take_most_dissimilar (infer.py:118-121): dist_i = 1 - mean_j cos(f_i, f_j) (F.cosine_similarity: every norm clamped at
+// 1e-8) or mean_j ||f_i - f_j||.  One CTA per i.
+__global__ void __launch_bounds__(256) mean_distance_kernel(const float* __restrict__ f, int N, int F, int measure,
+                                                            float* __restrict__ out) {
+    extern __shared__ float s_fi[];
+    __shared__ float s_red[8];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int k = tid; k < F; k += blockDim.x) s_fi[k] = f[static_cast<int64_t>(i) * F + k];
+    __syncthreads();
+    float ni2 = 0.0f;
+    if (measure == 0)
+        for (int k = 0; k < F; ++k) ni2 = fmaf(s_fi[k], s_fi[k], ni2);
+    float acc = 0.0f;
+    for (int j = wid; j < N; j += 8) {                     // one warp per partner row
+        const float* fj = f + static_cast<int64_t>(j) * F;
+        float a = 0.0f, b = 0.0f;
+        for (int k = lane; k < F; k += 32) {
+            const float x = s_fi[k], y = __ldg(fj + k);
+            if (measure == 0) { a = fmaf(x, y, a); b = fmaf(y, y, b); }
+            else { const float dlt = x - y; a = fmaf(dlt, dlt, a); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) acc += measure == 0 ? a / (fmaxf(sqrtf(ni2), 1e-8f) * fmaxf(sqrtf(b), 1e-8f)) : sqrtf(a);
+    }
+    if (lane == 0) s_red[wid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        const float mean = t / static_cast<float>(N);
+        out[i] = measure == 0 ? 1.0f - mean : mean;
+    }
+}
+
 }  // namespace
+
+extern "C" int vittf_topk_voxels(const float* maps, int n_maps, int64_t n, int K, long long* out_idx, float* out_thr, void* stream) {
+    VITTF_REQUIRE(maps && out_idx && n_maps > 0 && n > 0, "vittf_topk_voxels: bad arguments");
+    VITTF_REQUIRE(K > 0 && K <= TOPK_MAX && K <= n, "vittf_topk_voxels: K=%d must be in [1, min(%d, n)]", K, TOPK_MAX);
+    topk_voxels_kernel<<<n_maps, 512, 0, static_cast<cudaStream_t>(stream)>>>(maps, n, K, out_idx, out_thr);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
+
+extern "C" int vittf_mean_pairwise_distance(const float* feats, int N, int F, int measure, float* out, void* stream) {
+    VITTF_REQUIRE(feats && out && N > 0 && F > 0 && F <= 8192, "vittf_mean_pairwise_distance: bad arguments");
+    VITTF_REQUIRE(measure == 0 || measure == 1, "vittf_mean_pairwise_distance: measure must be 0 (cosine) or 1 (euclidean)");
+    mean_distance_kernel<<<N, 256, F * sizeof(float), static_cast<cudaStream_t>(stream)>>>(feats, N, F, measure, out);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
 
 extern "C" int vittf_binary_erosion(const uint8_t* mask, int W, int H, int D, int connectivity, uint8_t* out, void* stream) {
     VITTF_REQUIRE(mask && out && mask != out, "vittf_binary_erosion: null or aliased pointers");

@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(256) sim_upsample_kernel(UpParams q) {
             inv_norm = 1.0f / fmaxf(sqrtf(__ldg(q.gram + idx[0])), 1e-12f);
         }
         for (int c = 0; c < q.C; ++c) {
-            float red = q.mode == VITTF_SIM_REFNTF ? 0.0f : -INFINITY;
+            const bool mean_mode = q.mode == VITTF_SIM_REFNTF || q.mode == VITTF_SIM_CLAMP_MEAN;
+            float red = mean_mode ? 0.0f : -INFINITY;
             for (int a = s_off[c]; a < s_off[c + 1]; ++a) {
                 const float* da = q.dots + static_cast<int64_t>(a) * n_lr;
                 float s = 0.0f;
@@ -587,12 +588,14 @@ __global__ void __launch_bounds__(256) sim_upsample_kernel(UpParams q) {
                     if (wgt[k] != 0.0f) s = fmaf(wgt[k], __ldg(da + idx[k]), s);
                 if (q.mode == VITTF_SIM_REFNTF) {
                     red += pow_unit(s >= q.threshold ? s : 0.0f, q.exponent);
+                } else if (q.mode == VITTF_SIM_CLAMP_MEAN) {
+                    red += pow_unit(fminf(fmaxf(s, 0.0f), 1.0f), q.exponent);       // infer.py:104
                 } else {
                     red = fmaxf(red, s);  // clamp(0,1)**e is monotone: reduce first, transform once
                 }
             }
             float r;
-            if (q.mode == VITTF_SIM_REFNTF) r = red / static_cast<float>(s_off[c + 1] - s_off[c]);
+            if (mean_mode) r = red / static_cast<float>(s_off[c + 1] - s_off[c]);
             else r = pow_unit(fminf(fmaxf(red * inv_norm, 0.0f), 1.0f), q.exponent);
             q.out[static_cast<int64_t>(c) * n_out + o] = r;
         }
@@ -1185,9 +1188,9 @@ extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, i
                                   const int* class_offsets, int C, int W, int H, int D, int z0, int z1, int mode,
                                   float threshold, float exponent, float* out, void* stream) {
     VITTF_REQUIRE(dots && class_offsets && out, "vittf_sim_upsample: null pointer");
-    VITTF_REQUIRE(mode == VITTF_SIM_NS || mode == VITTF_SIM_REFNTF || mode == VITTF_SIM_LEGACY,
+    VITTF_REQUIRE(mode == VITTF_SIM_NS || mode == VITTF_SIM_REFNTF || mode == VITTF_SIM_LEGACY || mode == VITTF_SIM_CLAMP_MEAN,
                   "vittf_sim_upsample: unknown mode %d", mode);
-    VITTF_REQUIRE(mode == VITTF_SIM_REFNTF || gram, "vittf_sim_upsample: NS/LEGACY modes need the Gram planes");
+    VITTF_REQUIRE(mode == VITTF_SIM_REFNTF || mode == VITTF_SIM_CLAMP_MEAN || gram, "vittf_sim_upsample: NS/LEGACY modes need the Gram planes");
     VITTF_REQUIRE(C > 0 && A > 0 && W > 0 && H > 0 && D > 0 && z0 >= 0 && z1 > z0 && z1 <= D,
                   "vittf_sim_upsample: bad sizes (C=%d A=%d out=%dx%dx%d z=[%d,%d))", C, A, W, H, D, z0, z1);
     UpParams q{dots, gram, class_offsets, out, w, h, d, A, C, W, H, D, z0, z1, mode, threshold, exponent};

@@ -85,6 +85,54 @@ def sample_features3d(feat_vol, rel_coords, mode='nearest'):
     return torch.stack(outs).to(src_dev, src_dtype).contiguous()
 
 
+def resample_topk(feat_vol, sims, K=8, similarity_exponent=2.0, feature_sampling_mode='nearest'):
+    """infer.py:75-106.  feat_vol ([M,] F, W, H, D) (normalised) features, sims ([M,] C, A, W, H, D) per-annotation
+    similarity maps -> ([M,] C, A, W, H, D): every map is replaced by the mean over its K most similar voxels of
+    clamp(<f, f_k>, 0, 1) ** similarity_exponent.  The top-K search (with the reference's tie rule: first K voxels in
+    index order with s >= K-th largest), the feature gather and the K-prototype similarity run in libvittf_b200;
+    arithmetic is fp32 (the reference uses fp32 for K > 4 and the feature dtype otherwise)."""
+    from .similarity import similarity_maps
+    if sims.ndim == 5: sims = sims.unsqueeze(0)
+    if feat_vol.ndim == 4: feat_vol = make_5d(feat_vol)
+    src_dev, src_dtype = feat_vol.device, feat_vol.dtype
+    dev = _cuda_device(src_dev if src_dev.type == "cuda" else None)
+    M, C_, A = sims.shape[:3]
+    W, H, D = sims.shape[-3:]
+    if tuple(feat_vol.shape[-3:]) != (W, H, D):
+        raise ValueError("resample_topk: similarity maps must have the feature volume's resolution")
+    out = []
+    for m in range(M):
+        maps = sims[m].to(dev, torch.float32).reshape(C_ * A, W * H * D).contiguous()
+        flat, _ = ops.topk_voxels(maps, K)                                          # (C*A, K) flat voxel indices
+        top = torch.stack([flat // (H * D), (flat // D) % H, flat % D], dim=-1)     # :94  (C*A, K, 3)
+        ext = torch.tensor([[[W, H, D]]], dtype=torch.float32, device=dev)
+        rel = ((top.float() + 0.5) / ext * 2.0 - 1.0).reshape(-1, 3).contiguous()   # :95
+        fv = feat_vol[m].to(dev)
+        fv = (fv if fv.dtype in (torch.float16, torch.float32) else fv.float()).contiguous()
+        qf2 = ops.sample_prototypes(fv, rel, feature_sampling_mode)                 # :97  (C*A*K, F) fp32
+        print('resample_topk() qf2:', torch.Size((M, C_, A, K, qf2.size(-1))))
+        offs = torch.arange(0, C_ * A * K + 1, K, dtype=torch.int32, device=dev)    # groups of K prototypes -> mean (:106)
+        s2 = similarity_maps(fv, qf2.contiguous(), offs, mode="clamp_mean", exponent=similarity_exponent)
+        out.append(s2.view(C_, A, W, H, D))
+    res = torch.stack(out)
+    print('resample_topk() sims:', torch.Size((M, C_, A, K, W, H, D)))
+    return res.to(src_dtype).to(src_dev)
+
+
+def take_most_dissimilar(features, num_prototypes=35, measure='cosine'):
+    """infer.py:108-126: the `num_prototypes` rows of `features` (N, F) with the largest mean distance to all rows
+    (1 - mean cosine similarity, or mean Euclidean distance).  Distances are computed natively; the final top-k over
+    N scalars is torch glue like in the reference (its `sorted=False` leaves the row ORDER unspecified)."""
+    if features.size(0) <= num_prototypes: return features
+    if measure not in ('cosine', 'euclidean'):
+        raise ValueError(f'Unknown measure: {measure}')
+    dev = _cuda_device(features.device if features.is_cuda else None)
+    dist = ops.mean_pairwise_distance(features.to(dev, torch.float32).contiguous(), measure)
+    largest_dists, selected = torch.topk(dist, num_prototypes, largest=True, sorted=False)
+    print(f'Smallest distances (min: {largest_dists.min().item():.4f} avg: {largest_dists.mean().item():.4f}) vs average distance ({dist.mean().item():.4f})')
+    return features[selected.to(features.device)]
+
+
 def image_sizes(vol_shape, patch_size, feature_output_size):
     """infer.py:317-319"""
     ref_fact = sorted(vol_shape[-3:])[1] / feature_output_size

@@ -242,3 +242,27 @@ def binary_erosion(mask_u8, connectivity):
     check(load().vittf_binary_erosion(ptr(mask_u8), W, H, D, int(connectivity), ptr(out), stream_ptr(mask_u8.device)),
           "vittf_binary_erosion")
     return out
+
+
+def topk_voxels(maps, K):
+    """maps fp32 (n_maps, n) CUDA -> (int64 (n_maps, K) flat indices, fp32 (n_maps) thresholds) with the tie rule of
+    infer.py:92-93 (first K voxels in index order with value >= K-th largest value)."""
+    require_cuda(maps)
+    n_maps, n = maps.shape
+    idx = torch.empty(n_maps, K, dtype=torch.int64, device=maps.device)
+    thr = torch.empty(n_maps, dtype=torch.float32, device=maps.device)
+    check(load().vittf_topk_voxels(ptr(maps), n_maps, n, int(K), ptr(idx), ptr(thr), stream_ptr(maps.device)), "vittf_topk_voxels")
+    return idx, thr
+
+
+def mean_pairwise_distance(feats, measure):
+    """feats fp32 (N, F) CUDA -> fp32 (N): 1 - mean cosine similarity ('cosine') or mean Euclidean distance ('euclidean')."""
+    require_cuda(feats)
+    code = {"cosine": 0, "euclidean": 1}.get(measure)
+    if code is None:
+        raise ValueError(f'Unknown measure: {measure}')
+    N, F_ = feats.shape
+    out = torch.empty(N, dtype=torch.float32, device=feats.device)
+    check(load().vittf_mean_pairwise_distance(ptr(feats), N, F_, code, ptr(out), stream_ptr(feats.device)),
+          "vittf_mean_pairwise_distance")
+    return out

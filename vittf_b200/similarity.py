@@ -8,7 +8,7 @@ import torch
 
 from . import _lib, ops
 
-MODES = {"ns": _lib.SIM_NS, "refntf": _lib.SIM_REFNTF, "legacy": _lib.SIM_LEGACY}
+MODES = {"ns": _lib.SIM_NS, "refntf": _lib.SIM_REFNTF, "legacy": _lib.SIM_LEGACY, "clamp_mean": _lib.SIM_CLAMP_MEAN}
 
 
 def class_offsets(annotations, device):
@@ -33,9 +33,9 @@ def similarity_maps(feats, protos, offsets, out_shape=None, mode="ns", exponent=
     out_shape = lr if out_shape is None else tuple(out_shape)
     m = MODES[mode]
     if m != _lib.SIM_NS and out_shape != lr:
-        raise ValueError("refntf/legacy similarities are defined at feature resolution")
+        raise ValueError("refntf/legacy/clamp_mean similarities are defined at feature resolution")
     if lowres is None:
-        lowres = ops.sim_lowres(feats, protos, want_gram=(m != _lib.SIM_REFNTF))
+        lowres = ops.sim_lowres(feats, protos, want_gram=(m not in (_lib.SIM_REFNTF, _lib.SIM_CLAMP_MEAN)))
     dots, gram = lowres
     z0, z1 = (0, out_shape[2]) if z_range is None else z_range
     return ops.sim_upsample(dots, gram, lr, offsets, out_shape, m, threshold, exponent, z0, z1)
