@@ -123,3 +123,18 @@ def test_vit_full_depth_512(golden):
     cos = F.cosine_similarity(out, ref, dim=-1)
     assert cos.min().item() >= 0.995, cos.min().item()
     assert (out - ref).abs().max().item() < 0.05 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("arch,depth", [("vits16", 3), ("vitb16", 2), ("vitb8", 2)])
+def test_other_backbones_match_oracle(arch, depth):
+    """--dino-model vits16 / vitb16 (patch 16: the 224^2 position grid is 14 x 14 and is always
+    bicubically resampled) and vitb8 (768-d, 12 heads) through the same engine, against the fp32 oracle."""
+    from oracle import dino_vit, feature_volume as ofv, synth
+    from vittf_b200 import infer
+    patch = 16 if arch.endswith("16") else 8
+    vol, _ = synth.ct_volume((48, 40, 32), n_shells=4, seed=2)
+    model = dino_vit.build(arch, seed=1, depth=depth)
+    ref = ofv.feature_volume(vol, model, patch=patch, fos=8, batch_size=4)
+    out = infer.feature_volume(vol, model, patch, 8, batch_size=5).cpu()
+    assert out.shape == ref.shape and out.dtype == torch.float16
+    assert _cos_min(out, ref) >= 0.995
