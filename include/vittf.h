@@ -129,6 +129,12 @@ int vittf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, 
 /* softmax(Q K^T / 8) V per (image, head); qk (B*tokens, 2D) bf16, vt as written by epi 3,
  * out bf16 (B*tokens, D). */
 int vittf_attention(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads, void* stream);
+/* Same operator for q ALREADY multiplied by hd^-0.5 * log2(e) (the engine folds the factor into the Q rows of the qkv
+ * projection, vittf_b200/vit.py): a max-free first pass (p = 2^score, no running maximum) and a second, online-softmax pass
+ * over the CTAs whose rows left the safe exponent range (flags in `workspace`, vittf_attention_workspace_bytes).          */
+int64_t vittf_attention_workspace_bytes(int B, int tokens, int heads);
+int vittf_attention_prescaled(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads,
+                              void* workspace, int64_t workspace_bytes, void* stream);
 /* LayerNorm(eps=1e-6) over the last dim: x fp32 (rows, D) -> y bf16 */
 int vittf_layernorm(const float* x, const float* w, const float* b, void* y_bf16, int64_t rows, int D, void* stream);
 /* slices -> tokens fp32 (B, 1+f0*f1, D) incl. cls/pos (see vittf_vit_k_features) */

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "vittf_accumulate_f16": (_i, [_p, _p, _i64, _p]),
     "vittf_gemm_bf16": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vittf_attention": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "vittf_attention_workspace_bytes": (_i64, [_i, _i, _i]),
+    "vittf_attention_prescaled": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i64, _p]),
     "vittf_layernorm": (_i, [_p, _p, _p, _p, _i64, _i, _p]),
     "vittf_patch_embed": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "vittf_sample_prototypes": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _p]),

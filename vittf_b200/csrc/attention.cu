@@ -49,6 +49,7 @@ struct AttnParams {
     __nv_bfloat16* out;
     int tokens, heads, D;
     float scale_log2e;
+    int* flags;          // per-CTA: FAST writes 1 when a row left the safe exponent range, SAFE (re)computes flagged CTAs only
 };
 
 #ifdef ATTN_TRACE
@@ -120,8 +121,12 @@ __device__ __forceinline__ constexpr bool poly_slot(int pair) {
     return POLY_NUM > 0 && (r + 1) * POLY_NUM / POLY_EVERY_V != r * POLY_NUM / POLY_EVERY_V;
 }
 
+// FAST = true: the max-free first pass (see the header comment); FAST = false: online-softmax with running row max.
+template <bool FAST>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, AttnParams p) {
+    const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (!FAST && p.flags != nullptr && p.flags[cta_id] == 0) return;       // second pass: only CTAs the first pass flagged
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_q = smem;
@@ -267,9 +272,92 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             const uint32_t t_s = tmem_base + lane_base + COL_S + t * 128;
             const uint32_t t_p = tmem_base + lane_base + COL_P + t * 64;
             const uint32_t t_o = tmem_base + lane_base + COL_O + t * 64;
+            float l = 0.0f;
+            if constexpr (FAST) {
+                // ---- max-free pass: q arrives pre-scaled, so a score IS the base-2 exponent and p = 2^s needs no running
+                // maximum as long as the exponents stay inside what bf16 P and fp32 O / l can hold; rows that leave that
+                // range are detected on l afterwards and their CTA is redone by the safe kernel.  Per score: MUFU (or the
+                // FMA-pipe polynomial), half an FADD2 and half an F2FP -- no scale FMA, no max, no rescale logic.
+                float l_f = 0.0f;
+                const int bar_mine_f = 1 + q * 2 + t, bar_other_f = 1 + q * 2 + (t ^ 1);
+                if (PINGPONG && has_b && t == 1) named_arrive(bar_other_f, 64);   // tile A goes first
+                for (int j = 0; j < nfull; ++j) {
+                    if (q == 0 && lane == 0) TRACE(t, j, 0);
+                    ptx::mbar_wait(&s_full[t], j & 1);
+                    if (q == 0 && lane == 0) TRACE(t, j, 1);
+                    ptx::tc_fence_after();
+                    uint32_t s[4][32];
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(t_s + ch * 32, s[ch]);
+                    ptx::tc_wait_ld();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&s_free[t]);          // the MMA warp may overwrite S with the next block's scores
+                    if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);   // P buffer free again (normally long since)
+                    if (PINGPONG && has_b) named_sync(bar_mine_f, 64);
+                    if (q == 0 && lane == 0) TRACE(t, j, 2);
+                    ptx::F2 sums[4] = {{0ull}, {0ull}, {0ull}, {0ull}};
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float x0 = __uint_as_float(s[ch][2 * i]), x1 = __uint_as_float(s[ch][2 * i + 1]);
+                            float p0, p1;
+                            if (poly_slot(ch * 16 + i)) {
+                                exp2_poly2(fminf(x0, 126.0f), fminf(x1, 126.0f), p0, p1);   // 2^126 still trips the range check
+                            } else {
+                                p0 = ptx::ex2_approx(x0);
+                                p1 = ptx::ex2_approx(x1);
+                            }
+                            sums[i & 3] = ptx::f2_add(sums[i & 3], ptx::f2_make(p0, p1));
+                            pk[i] = ptx::pack_bf16x2(p0, p1);
+                        }
+                        ptx::tmem_st16(t_p + ch * 16, pk);
+                        if (PINGPONG && ch == HANDOVER_CH && has_b && !(t == 1 && j == nkv - 1)) named_arrive(bar_other_f, 64);
+                    }
+                    float a0, a1, b0, b1;
+                    ptx::f2_get(ptx::f2_add(sums[0], sums[1]), a0, a1);
+                    ptx::f2_get(ptx::f2_add(sums[2], sums[3]), b0, b1);
+                    l_f += (a0 + a1) + (b0 + b1);
+                    ptx::tc_wait_st();
+                    if (q == 0 && lane == 0) TRACE(t, j, 3);
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&p_ready[t]);
+                }
+                if (tail > 0) {
+                    const int j = nfull;
+                    ptx::mbar_wait(&s_full[t], j & 1);
+                    ptx::tc_fence_after();
+                    if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);
+                    if (PINGPONG && has_b) named_sync(bar_mine_f, 64);
+                    float sum = 0.0f;
+                    for (int c0 = 0; c0 < tail_n; c0 += 16) {
+                        uint32_t v[16], pk[8];
+                        ptx::tmem_ld16(t_s + c0, v);
+                        ptx::tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float p0 = c0 + 2 * i < tail ? ptx::ex2_approx(__uint_as_float(v[2 * i])) : 0.0f;
+                            const float p1 = c0 + 2 * i + 1 < tail ? ptx::ex2_approx(__uint_as_float(v[2 * i + 1])) : 0.0f;
+                            sum += p0 + p1;
+                            pk[i] = ptx::pack_bf16x2(p0, p1);
+                        }
+                        ptx::tmem_st8(t_p + (c0 >> 1), pk);
+                    }
+                    l_f += sum;
+                    if (PINGPONG && has_b && t == 0) named_arrive(bar_other_f, 64);
+                    ptx::tc_wait_st();
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&p_ready[t]);
+                }
+                // 2^-100 < l < 2^100 bounds every p (and p * v) far away from fp32 overflow and from total underflow;
+                // anything else (inf, NaN, 0) sends the CTA to the safe pass.  Padding rows beyond `tokens` are ignored.
+                const bool row_live = q0 + t * BQ + q * 32 + lane < p.tokens;
+                if (row_live && !(l_f > 7.888609052210118e-31f && l_f < 1.2676506002282294e30f)) p.flags[cta_id] = 1;
+                l = l_f;
+            } else {
             const float c = p.scale_log2e;
             float m_used = -INFINITY;
-            float l = 0.0f;
             // Ping-pong on the exponential (MUFU) pipe: warps 4+q (tile A) and 8+q (tile B) share an SM sub-partition.
             // Left alone they run their exponentials at the same time (pipe oversubscribed) and their TMEM loads /
             // row maxima at the same time (pipe idle); strict alternation keeps the pipe busy.
@@ -397,6 +485,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&p_ready[t]);
             }
+            }
             // ---- output: O / l -> bf16, token-major (B*tokens, D) at column head*64 ----
             ptx::mbar_wait(&pv_done[t], (nkv - 1) & 1);   // the last P V has landed in O
             ptx::tc_fence_after();
@@ -429,12 +518,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 
 }  // namespace
 
-extern "C" int vittf_attention(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads,
-                               void* stream) {
-    VITTF_REQUIRE(qk && vt && out, "vittf_attention: null pointer");
-    VITTF_REQUIRE(B > 0 && tokens > 0 && heads > 0, "vittf_attention: empty problem");
-    VITTF_REQUIRE(tok_pad >= tokens && tok_pad % 8 == 0, "vittf_attention: tok_pad=%d must be >= tokens and a multiple of 8",
-                  tok_pad);
+namespace {
+int attention_launch(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads, float scale,
+                     int* flags, bool fast, cudaStream_t stream) {
     const int D = heads * HD;
     CUtensorMap tm_qk, tm_vt;
     {
@@ -451,15 +537,53 @@ extern "C" int vittf_attention(const void* qk, const void* vt, void* out, int B,
     }
     static bool configured = false;
     if (!configured) {
-        VITTF_CHECK_CUDA(
-            cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        VITTF_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+        VITTF_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
         configured = true;
     }
-    AttnParams p{static_cast<__nv_bfloat16*>(out), tokens, heads, D, 0.125f * 1.4426950408889634f};
+    AttnParams p{static_cast<__nv_bfloat16*>(out), tokens, heads, D, scale, flags};
     dim3 grid(ceil_div(tokens, 2 * BQ), heads, B);
-    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tm_qk, tm_vt, p);
+    if (fast) attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm_qk, tm_vt, p);
+    else attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm_qk, tm_vt, p);
     VITTF_CHECK_CUDA(cudaGetLastError());
     vittf_count_launches(1);
+    return VITTF_OK;
+}
+}  // namespace
+
+extern "C" int64_t vittf_attention_workspace_bytes(int B, int tokens, int heads) {
+    if (B <= 0 || tokens <= 0 || heads <= 0) return -1;
+    return static_cast<int64_t>(ceil_div(tokens, 2 * BQ)) * heads * B * sizeof(int);
+}
+
+// q pre-scaled by hd^-0.5 * log2(e) (the engine folds it into the qkv weights): max-free first pass + safe pass over the
+// CTAs it flagged (normally none: the second launch exits after one flag read per CTA).
+extern "C" int vittf_attention_prescaled(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads,
+                                         void* workspace, int64_t workspace_bytes, void* stream) {
+    VITTF_REQUIRE(qk && vt && out && workspace, "vittf_attention_prescaled: null pointer");
+    VITTF_REQUIRE(B > 0 && tokens > 0 && heads > 0, "vittf_attention_prescaled: empty problem");
+    VITTF_REQUIRE(tok_pad >= tokens && tok_pad % 8 == 0, "vittf_attention_prescaled: tok_pad=%d must be >= tokens and a multiple of 8",
+                  tok_pad);
+    const int64_t need = vittf_attention_workspace_bytes(B, tokens, heads);
+    VITTF_REQUIRE(workspace_bytes >= need, "vittf_attention_prescaled: workspace of %lld B is smaller than the %lld B required",
+                  (long long)workspace_bytes, (long long)need);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int* flags = static_cast<int*>(workspace);
+    static const bool safe_only = getenv("VITTF_ATTN_SAFE_ONLY") != nullptr;      // A/B switch
+    if (safe_only) return attention_launch(qk, vt, out, B, tokens, tok_pad, heads, 1.0f, nullptr, false, s);
+    VITTF_CHECK_CUDA(cudaMemsetAsync(flags, 0, need, s));
+    VITTF_CHECK(attention_launch(qk, vt, out, B, tokens, tok_pad, heads, 1.0f, flags, true, s));
+    return attention_launch(qk, vt, out, B, tokens, tok_pad, heads, 1.0f, flags, false, s);
+}
+
+extern "C" int vittf_attention(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads,
+                               void* stream) {
+    VITTF_REQUIRE(qk && vt && out, "vittf_attention: null pointer");
+    VITTF_REQUIRE(B > 0 && tokens > 0 && heads > 0, "vittf_attention: empty problem");
+    VITTF_REQUIRE(tok_pad >= tokens && tok_pad % 8 == 0, "vittf_attention: tok_pad=%d must be >= tokens and a multiple of 8",
+                  tok_pad);
+    VITTF_CHECK(attention_launch(qk, vt, out, B, tokens, tok_pad, heads, 0.125f * 1.4426950408889634f, nullptr, false,
+                                 static_cast<cudaStream_t>(stream)));
 #ifdef ATTN_TRACE
     if (getenv("VITTF_ATTN_TRACE_DUMP")) {
         static long long h[3 * 40 * 4];

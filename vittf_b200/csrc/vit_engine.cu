@@ -32,6 +32,8 @@ struct Workspace {
     __nv_bfloat16* vt;    // (B*heads*64, tok_pad)
     __nv_bfloat16* att;   // attention output (M, D)
     __nv_bfloat16* hid;   // MLP hidden (M, 4D)
+    void* attn_ws;        // per-CTA flags of the two-pass attention
+    int64_t attn_ws_bytes;
     int64_t vt_bytes;
     int64_t total;
 };
@@ -49,6 +51,8 @@ Workspace carve(const vittf_vit_config& c, int batch, int tokens, uint8_t* base)
     w.vt = reinterpret_cast<__nv_bfloat16*>(take(w.vt_bytes));
     w.att = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
     w.hid = reinterpret_cast<__nv_bfloat16*>(take(M * c.mlp_hidden * 2));
+    w.attn_ws_bytes = vittf_attention_workspace_bytes(batch, tokens, c.num_heads);
+    w.attn_ws = take(w.attn_ws_bytes);
     w.total = off;
     return w;
 }
@@ -161,7 +165,7 @@ extern "C" int vittf_vit_k_features(vittf_vit* v, const void* vol, int vol_dtype
         { ScopedTimer t(v, 1, s);
           VITTF_CHECK(vittf_gemm_bf16(w.xn, bw.qkv_w, bw.qkv_b, w.qk, w.vt, M, 3 * D, D, VITTF_EPI_QKV_SPLIT, tokens, tok_pad, stream)); }
         { ScopedTimer t(v, 0, s);
-          VITTF_CHECK(vittf_attention(w.qk, w.vt, w.att, B, tokens, tok_pad, c.num_heads, stream)); }
+          VITTF_CHECK(vittf_attention_prescaled(w.qk, w.vt, w.att, B, tokens, tok_pad, c.num_heads, w.attn_ws, w.attn_ws_bytes, stream)); }
         { ScopedTimer t(v, 1, s);
           VITTF_CHECK(vittf_gemm_bf16(w.att, bw.proj_w, bw.proj_b, w.x, nullptr, M, D, D, VITTF_EPI_BIAS_RESID_F32, tokens, tok_pad, stream)); }
         VITTF_CHECK(vittf_layernorm(w.x, bw.ln2_w, bw.ln2_b, w.xn, M, D, stream));

@@ -59,6 +59,17 @@ def attention(qk, vt, batch, tokens, heads, tok_pad):
     return out
 
 
+def attention_prescaled(qk, vt, batch, tokens, heads, tok_pad, return_flags=False):
+    """softmax(q k^T) v for q already multiplied by hd^-0.5 * log2(e): max-free first pass + safe pass over flagged CTAs."""
+    require_cuda(qk, vt)
+    out = torch.empty(batch * tokens, heads * 64, dtype=torch.bfloat16, device=qk.device)
+    need = load().vittf_attention_workspace_bytes(batch, tokens, heads)
+    ws = torch.empty(need // 4, dtype=torch.int32, device=qk.device)
+    check(load().vittf_attention_prescaled(ptr(qk), ptr(vt), ptr(out), batch, tokens, tok_pad, heads, ptr(ws), need,
+                                           stream_ptr(qk.device)), "vittf_attention_prescaled")
+    return (out, ws) if return_flags else out
+
+
 def layernorm(x, w, b):
     require_cuda(x, w, b)
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)

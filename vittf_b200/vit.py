@@ -84,9 +84,17 @@ class VitEngine:
         pw, pb = fold_patch_embed(proj.weight, proj.bias)
         self.patch_w, self.patch_b = f32(pw), f32(pb)
         arr = (BlockWeights * self.depth)()
+        # the engine's attention (vittf_attention_prescaled) takes q pre-scaled by hd^-0.5 * log2(e), so that a score is
+        # directly the base-2 exponent: fold the factor into the Q rows of the qkv projection once, in fp32, before the
+        # bf16 copy (K and V rows -- and with them the hooked K features -- are untouched)
+        head_dim = self.embed_dim // self.num_heads
+        q_scale = torch.ones(3 * self.embed_dim, dtype=torch.float32)
+        q_scale[:self.embed_dim] = head_dim ** -0.5 * math.log2(math.e)
         for i, blk in enumerate(blocks):
+            qkv_w = blk.attn.qkv.weight.detach().float().cpu() * q_scale[:, None]
+            qkv_b = blk.attn.qkv.bias.detach().float().cpu() * q_scale
             fields = dict(ln1_w=f32(blk.norm1.weight), ln1_b=f32(blk.norm1.bias),
-                          qkv_w=bf16(blk.attn.qkv.weight), qkv_b=f32(blk.attn.qkv.bias),
+                          qkv_w=bf16(qkv_w), qkv_b=f32(qkv_b),
                           proj_w=bf16(blk.attn.proj.weight), proj_b=f32(blk.attn.proj.bias),
                           ln2_w=f32(blk.norm2.weight), ln2_b=f32(blk.norm2.bias),
                           fc1_w=bf16(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias),
