@@ -281,6 +281,10 @@ def main():
     gemm_ms, gemm_n = timing["gemm"]
     n_img = 3 * size
     total_flops = needed_flops_per_image(arch, tokens) * n_img
+    # DRAM bytes of one attention launch from the committed `ncu --set full` capture (profiles/r1_ncu_attention_v5.json:
+    # dram__bytes_read.sum + dram__bytes_write.sum = 305.4 + 84.4 MB at ViT-S/8, 32 slices of 4097 tokens); the algorithmic
+    # bytes of that launch (q, k, V^T read once, output written once) are 4 * B * tokens * D * 2 = 403 MB
+    traffic = 389.78e6 if (arch == "vits8" and batch == 32 and tokens == 4097) else None
     out = {
         "metric": "ms per volume end-to-end (ViT feats + similarity)", "value": ms_dev, "unit": "ms", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": False,
@@ -290,7 +294,8 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"kernel": "attention_kernel (tcgen05 flash attention, hd 64)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                     "traffic": None, "peak_source": peak_src, "avg_launch_ms": att_avg_ms, "launches_timed": int(att_n),
+                     "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
+                     "traffic_source": "profiles/r1_ncu_attention_v5.json" if traffic else None, "peak_source": peak_src, "avg_launch_ms": att_avg_ms, "launches_timed": int(att_n),
                      "share_of_step": att_ms / (ms_dev * args.steps) if ms_dev else None,
                      "gemm_share_of_step": gemm_ms / (ms_dev * args.steps) if ms_dev else None},
         "vit_tflops_needed": total_flops / world / (ms_dev * 1e-3) / 1e12 * world,
