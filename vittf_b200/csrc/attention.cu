@@ -49,7 +49,8 @@ struct AttnParams {
     __nv_bfloat16* out;
     int tokens, heads, D;
     float scale_log2e;
-    int* flags;          // per-CTA: FAST writes 1 when a row left the safe exponent range, SAFE (re)computes flagged CTAs only
+    int* flags;          // per item: FAST writes 1 when a row left the safe exponent range, SAFE (re)computes flagged items only
+    int n_items, units;  // items = (image, head, unit of 2 query tiles), unit fastest
 };
 
 #ifdef ATTN_TRACE
@@ -122,85 +123,107 @@ __device__ __forceinline__ constexpr bool poly_slot(int pair) {
 }
 
 // FAST = true: the max-free first pass (see the header comment); FAST = false: online-softmax with running row max.
+// PERSISTENT: gridDim.x CTAs (one per SM) walk the work items item = blockIdx.x, + gridDim.x, ...; an item is the pair of
+// 128-row query tiles `unit` of one (image, head).  Barriers, the K/V ring and TMEM live across items, so the loads and the
+// first score MMA of the next item overlap the epilogue of the current one, and no CTA is launched per item.
 template <bool FAST>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     attention_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, AttnParams p) {
-    const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    if (!FAST && p.flags != nullptr && p.flags[cta_id] == 0) return;       // second pass: only CTAs the first pass flagged
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* s_q = smem;
-    uint8_t* s_kv = smem + 2 * Q_TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + KV_STAGES * KV_STAGE_BYTES);
-    uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = kv_full + KV_STAGES;
-    uint64_t* s_full = kv_empty + KV_STAGES;  // [2] scores of the next block are in TMEM
-    uint64_t* s_free = s_full + 2;            // [2] all 128 rows of S are in registers
-    uint64_t* p_ready = s_free + 2;           // [2] P written
-    uint64_t* pv_done = p_ready + 2;          // [2] P V finished (P buffer reusable, O stable)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    // Every role re-derives its pointers and block counts from the kernel parameters behind an opaque zero (ROLE_LOCALS):
+    // values computed once up here and used by all roles would stay live across the setmaxnreg boundaries, and ptxas
+    // parks them in local memory -- reloads in the MMA issuers' loop are exactly what the persistent form must avoid.
+#define ROLE_LOCALS                                                                                                      \
+    uint32_t z_ = 0;                                                                                                     \
+    asm volatile("" : "+r"(z_));                                                                                         \
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + z_ + 1023) & ~uintptr_t(1023));  \
+    uint8_t* s_q = smem;                                                                                                 \
+    uint8_t* s_kv = smem + 2 * Q_TILE_BYTES;                                                                             \
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + KV_STAGES * KV_STAGE_BYTES);                                     \
+    uint64_t* q_full = bars;                  /* Q tiles of the item have landed */                                      \
+    uint64_t* q_empty = bars + 1;             /* both tiles have issued their last score MMA of the item */              \
+    uint64_t* kv_full = bars + 2;                                                                                        \
+    uint64_t* kv_empty = kv_full + KV_STAGES;                                                                            \
+    uint64_t* s_full = kv_empty + KV_STAGES;  /* [2] scores of the next block are in TMEM */                             \
+    uint64_t* s_free = s_full + 2;            /* [2] all 128 rows of S are in registers */                               \
+    uint64_t* p_ready = s_free + 2;           /* [2] P written */                                                        \
+    uint64_t* pv_done = p_ready + 2;          /* [2] P V finished (P buffer reusable, O stable) */                       \
+    uint64_t* o_free = pv_done + 2;           /* [2] the epilogue has read O: the next item may overwrite it */          \
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);                                                       \
+    /* keys: nfull blocks of 128 + one tail block that is only as wide as it has to be (tokens = 4097 = 32 * 128 + 1 */  \
+    /* at 512^2 input: the tail costs a 128x16 MMA instead of a 33rd full block) */                                      \
+    const int tokens_ = p.tokens + static_cast<int>(z_);                                                                 \
+    const int nfull = tokens_ / BKV;                                                                                     \
+    const int tail = tokens_ - nfull * BKV;         /* valid keys in the tail block (0 = none) */                        \
+    const int tail_n = (tail + 15) & ~15;            /* its MMA N (scores) / K (P V) extent */                            \
+    const int nkv = nfull + (tail > 0 ? 1 : 0);                                                                          \
+    /* every role walks the same item sequence; the safe pass only visits items the first pass flagged */                \
+    auto visit = [&](int item) { return FAST || p.flags == nullptr || p.flags[item] != 0; };                             \
+    auto two_tiles = [&](int item) { return (item % p.units) * 2 * BQ + BQ < p.tokens; };                                \
+    (void)s_q; (void)q_full; (void)q_empty; (void)kv_full; (void)kv_empty; (void)s_full; (void)s_free; (void)p_ready;     \
+    (void)pv_done; (void)o_free; (void)tmem_slot; (void)tail_n; (void)nkv; (void)visit; (void)two_tiles
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
     const int lane = threadIdx.x & 31;
-    const int unit = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
-    const int q0 = unit * 2 * BQ;
-    const bool has_b = q0 + BQ < p.tokens;
-    const int n_tiles = has_b ? 2 : 1;
-    // keys: nfull blocks of 128 + one tail block that is only as wide as it has to be (tokens = 4097 = 32 * 128 + 1
-    // at 512^2 input: the tail costs a 128x16 MMA instead of a 33rd full block)
-    const int nfull = p.tokens / BKV;
-    const int tail = p.tokens - nfull * BKV;         // valid keys in the tail block (0 = none)
-    const int tail_n = (tail + 15) & ~15;            // its MMA N (scores) / K (P V) extent
-    const int nkv = nfull + (tail > 0 ? 1 : 0);
-
+    {
+        ROLE_LOCALS;
     if (threadIdx.x == 0) {   // one-time setup, not on the hot path
         ptx::mbar_init(q_full, 1);
+        ptx::mbar_init(q_empty, 2);
         for (int i = 0; i < KV_STAGES; ++i) {
             ptx::mbar_init(&kv_full[i], 1);
-            ptx::mbar_init(&kv_empty[i], n_tiles);   // one tcgen05.commit per query tile
+            ptx::mbar_init(&kv_empty[i], 2);         // one tcgen05.commit per query tile (tile B's issuer shadows one-tile items)
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s_full[i], 1);
             ptx::mbar_init(&s_free[i], 128);
             ptx::mbar_init(&p_ready[i], 128);
             ptx::mbar_init(&pv_done[i], 1);
+            ptx::mbar_init(&o_free[i], 128);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    // register re-balancing: the producer / MMA / allocator warpgroup needs few registers, the two softmax
-    // warpgroups hold a whole 128-wide score row per thread
-    // (each role region below is entered right after its own setmaxnreg so that ptxas sees the budget)
 
     // Roles are dispatched per WARP (uniform) and the single issuing lane is chosen with elect.sync: a branch on
     // threadIdx.x would make ptxas wrap every TMA / MMA instruction in a divergence ("waterfall") loop, because
     // their descriptor operands must live in uniform registers.  Only that one lane polls the mbarriers -- a full
     // warp spinning on try_wait measurably starves the softmax warps that share its scheduler.
+    // Register re-balancing: the producer / MMA / allocator warpgroup needs few registers, the two softmax warpgroups
+    // hold a whole 128-wide score row per thread.
     if (warp < 4) {
-      ptx::setmaxnreg_dec<64>();
+      ptx::setmaxnreg_dec<64>();     // the CTA owns 384 x 168 registers: 128 x (168 - 64) released >= 256 x (216 - 168) claimed below
       if (warp == 0) {
         // ---------------- TMA producer (one elected lane) ----------------
         if (ptx::elect_one()) {
+            ROLE_LOCALS;
             ptx::prefetch_tmap(&tm_qk);
             ptx::prefetch_tmap(&tm_vt);
-            ptx::mbar_arrive_expect_tx(q_full, n_tiles * Q_TILE_BYTES);
-            for (int t = 0; t < n_tiles; ++t)
-                ptx::tma_load_3d(s_q + t * Q_TILE_BYTES, &tm_qk, q_full, head * HD, q0 + t * BQ, img);
-            const int vt_row = (img * p.heads + head) * HD;
-            for (int j = 0; j < nkv; ++j) {
-                const int st = j % KV_STAGES;
-                ptx::mbar_wait(&kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
-                uint8_t* dst = s_kv + st * KV_STAGE_BYTES;
-                ptx::mbar_arrive_expect_tx(&kv_full[st], KV_STAGE_BYTES);
-                ptx::tma_load_3d(dst, &tm_qk, &kv_full[st], p.D + head * HD, j * BKV, img);
-                ptx::tma_load_2d(dst + K_TILE_BYTES, &tm_vt, &kv_full[st], j * BKV, vt_row);
-                ptx::tma_load_2d(dst + K_TILE_BYTES + V_HALF_BYTES, &tm_vt, &kv_full[st], j * BKV + 64, vt_row);
+            int g = 0, np = 0;               // key blocks / items loaded so far
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                if (!visit(item)) continue;
+                const int unit = item % p.units, head = (item / p.units) % p.heads, img = item / (p.units * p.heads);
+                const int q0 = unit * 2 * BQ;
+                const int n_tiles = q0 + BQ < p.tokens ? 2 : 1;
+                ptx::mbar_wait_quiet(q_empty, (np & 1) ^ 1);           // the previous item's score MMAs are done with Q
+                ptx::mbar_arrive_expect_tx(q_full, n_tiles * Q_TILE_BYTES);
+                for (int t = 0; t < n_tiles; ++t)
+                    ptx::tma_load_3d(s_q + t * Q_TILE_BYTES, &tm_qk, q_full, head * HD, q0 + t * BQ, img);
+                const int vt_row = (img * p.heads + head) * HD;
+                for (int j = 0; j < nkv; ++j, ++g) {
+                    const int st = g % KV_STAGES;
+                    ptx::mbar_wait_quiet(&kv_empty[st], ((g / KV_STAGES) & 1) ^ 1);
+                    uint8_t* dst = s_kv + st * KV_STAGE_BYTES;
+                    ptx::mbar_arrive_expect_tx(&kv_full[st], KV_STAGE_BYTES);
+                    ptx::tma_load_3d(dst, &tm_qk, &kv_full[st], p.D + head * HD, j * BKV, img);
+                    ptx::tma_load_2d(dst + K_TILE_BYTES, &tm_vt, &kv_full[st], j * BKV, vt_row);
+                    ptx::tma_load_2d(dst + K_TILE_BYTES + V_HALF_BYTES, &tm_vt, &kv_full[st], j * BKV + 64, vt_row);
+                }
+                ++np;
             }
         }
       } else if ((warp == 1 || warp == 3) && ptx::elect_one()) {
@@ -208,40 +231,57 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         // One thread per tile keeps the two tiles decoupled (an in-order issuer blocked on tile B's barrier cannot
         // delay tile A) and its instruction stream short: the clock64 traces showed the single issuing thread, not
         // the tensor pipe, on the critical path (~250 dependent uniform-datapath instructions per key block).
+        ROLE_LOCALS;
+        const uint32_t tmem_base = *tmem_slot;
         const int t = warp >> 1;
-        if (t < n_tiles) {
-            constexpr uint32_t idesc_s_full = ptx::idesc_bf16_f32(BQ, BKV);
-            const uint32_t idesc_s_tail = ptx::idesc_bf16_f32(BQ, tail_n);
-            constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, HD);
-            constexpr uint32_t STAGE_DESC = KV_STAGE_BYTES >> 4;    // descriptor address units are 16 B
-            constexpr uint32_t V_DESC = K_TILE_BYTES >> 4, VH_DESC = V_HALF_BYTES >> 4;
-            const uint32_t d_s = tmem_base + COL_S + t * 128, d_o = tmem_base + COL_O + t * 64, a_p = tmem_base + COL_P + t * 64;
-            const uint64_t q_desc = ptx::smem_desc_k_sw128(ptx::smem_u32(s_q) + t * Q_TILE_BYTES);
-            const uint64_t kv_desc0 = ptx::smem_desc_k_sw128(ptx::smem_u32(s_kv));
-            auto issue_s = [&](uint64_t k_desc, uint32_t idesc) {
+        constexpr uint32_t idesc_s_full = ptx::idesc_bf16_f32(BQ, BKV);
+        const uint32_t idesc_s_tail = ptx::idesc_bf16_f32(BQ, tail_n);
+        constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(BQ, HD);
+        constexpr uint32_t STAGE_DESC = KV_STAGE_BYTES >> 4;    // descriptor address units are 16 B
+        constexpr uint32_t V_DESC = K_TILE_BYTES >> 4, VH_DESC = V_HALF_BYTES >> 4;
+        const uint32_t d_s = tmem_base + COL_S + t * 128, d_o = tmem_base + COL_O + t * 64, a_p = tmem_base + COL_P + t * 64;
+        const uint64_t q_desc = ptx::smem_desc_k_sw128(ptx::smem_u32(s_q) + t * Q_TILE_BYTES);
+        const uint64_t kv_desc0 = ptx::smem_desc_k_sw128(ptx::smem_u32(s_kv));
+        auto issue_s = [&](uint64_t k_desc, uint32_t idesc) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) ptx::umma_ss(d_s, q_desc + 2 * k, k_desc + 2 * k, idesc, k != 0);
-            };
-            ptx::mbar_wait(q_full, 0);
-            ptx::mbar_wait(&kv_full[0], 0);
+            for (int k = 0; k < HD / 16; ++k) ptx::umma_ss(d_s, q_desc + 2 * k, k_desc + 2 * k, idesc, k != 0);
+        };
+        int g = 0, np = 0;       // key blocks / items seen so far (shared barriers: every phase is waited on, in order)
+        int gt = 0, nt = 0;      // key blocks / items this tile has processed (its own barriers)
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            if (!visit(item)) continue;
+            const bool mine = t == 0 || two_tiles(item);
+            ptx::mbar_wait_quiet(q_full, np & 1);
+            if (!mine) {
+                // one-tile item: tile B's issuer only shadows the shared barriers so that their counts and phases stay uniform
+                for (int j = 0; j < nkv; ++j, ++g) {
+                    ptx::mbar_wait_quiet(&kv_full[g % KV_STAGES], (g / KV_STAGES) & 1);
+                    ptx::tc_commit(&kv_empty[g % KV_STAGES]);
+                }
+                ptx::tc_commit(q_empty);
+                ++np;
+                continue;
+            }
+            ptx::mbar_wait_quiet(&kv_full[g % KV_STAGES], (g / KV_STAGES) & 1);
+            if (nt > 0) ptx::mbar_wait_quiet(&s_free[t], (gt - 1) & 1);      // the previous item's last scores were read
             ptx::tc_fence_after();
-            issue_s(kv_desc0, nfull > 0 ? idesc_s_full : idesc_s_tail);
+            issue_s(kv_desc0 + (g % KV_STAGES) * STAGE_DESC, nfull > 0 ? idesc_s_full : idesc_s_tail);
             ptx::tc_commit(&s_full[t]);
-            int st = 0;                      // ring stage of key block j
-            uint32_t ring_phase = 0;         // parity of kv_full for stage st
-            for (int j = 0; j < nkv; ++j) {
-                const int st1 = st + 1 == KV_STAGES ? 0 : st + 1;
-                const uint32_t phase1 = st1 == 0 ? ring_phase ^ 1 : ring_phase;
+            if (nkv == 1) ptx::tc_commit(q_empty);
+            for (int j = 0; j < nkv; ++j, ++g) {
+                const int st = g % KV_STAGES, st1 = (g + 1) % KV_STAGES;
                 if (j + 1 < nkv) {           // S(j+1) as soon as block j's scores sit in registers
-                    ptx::mbar_wait(&kv_full[st1], phase1);
+                    ptx::mbar_wait_quiet(&kv_full[st1], ((g + 1) / KV_STAGES) & 1);
                     if (t == 0) TRACE(2, j, 0);
-                    ptx::mbar_wait(&s_free[t], j & 1);
+                    ptx::mbar_wait_quiet(&s_free[t], (gt + j) & 1);
                     ptx::tc_fence_after();
                     issue_s(kv_desc0 + st1 * STAGE_DESC, j + 1 < nfull ? idesc_s_full : idesc_s_tail);
                     ptx::tc_commit(&s_full[t]);
+                    if (j + 2 == nkv) ptx::tc_commit(q_empty);         // last score MMA of the item: Q may be replaced
                     if (t == 0) TRACE(2, j, 1);
                 }
-                ptx::mbar_wait(&p_ready[t], j & 1);
+                ptx::mbar_wait_quiet(&p_ready[t], (gt + j) & 1);
+                if (j == 0 && nt > 0) ptx::mbar_wait_quiet(&o_free[t], (nt - 1) & 1);   // the previous item's O has been read out
                 if (t == 0) TRACE(2, j, 2);
                 ptx::tc_fence_after();
                 const uint64_t v_desc = kv_desc0 + st * STAGE_DESC + V_DESC;
@@ -257,33 +297,50 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                 ptx::tc_commit(&pv_done[t]);
                 ptx::tc_commit(&kv_empty[st]);     // this tile is done with the stage (the barrier counts both tiles)
                 if (t == 0) TRACE(2, j, 3);
-                st = st1;
-                ring_phase = phase1;
             }
+            gt += nkv;
+            ++nt;
+            ++np;
         }
       }
     } else {
         ptx::setmaxnreg_inc<216>();
         // ---------------- softmax + output ----------------
+        ROLE_LOCALS;
+        const uint32_t tmem_base = *tmem_slot;
+        int last2 = -1;                                  // last two-tile item of this CTA (ends the ping-pong token chain)
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x)
+            if (visit(item) && two_tiles(item)) last2 = item;
         const int t = (warp - 4) >> 2;
-        if (t < n_tiles) {
-            const int q = warp & 3;
-            const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-            const uint32_t t_s = tmem_base + lane_base + COL_S + t * 128;
-            const uint32_t t_p = tmem_base + lane_base + COL_P + t * 64;
-            const uint32_t t_o = tmem_base + lane_base + COL_O + t * 64;
+        const int q = warp & 3;
+        const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t t_s = tmem_base + lane_base + COL_S + t * 128;
+        const uint32_t t_p = tmem_base + lane_base + COL_P + t * 64;
+        const uint32_t t_o = tmem_base + lane_base + COL_O + t * 64;
+        // Ping-pong on the exponential (MUFU) pipe: warps 4+q (tile A) and 8+q (tile B) share an SM sub-partition.
+        // Left alone they run their exponentials at the same time (pipe oversubscribed) and their TMEM loads /
+        // row maxima at the same time (pipe idle); strict alternation keeps the pipe busy.  The turn token is handed
+        // back and forth across items; tile B's very last block keeps it (nobody follows).
+        const int bar_mine = 1 + q * 2 + t, bar_other = 1 + q * 2 + (t ^ 1);
+        if (PINGPONG && last2 >= 0 && t == 1) named_arrive(bar_other, 64);   // tile A goes first
+        int gt = 0;              // key blocks this tile has processed
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            if (!visit(item)) continue;
+            // only what the block loop needs stays live through it (the loop body sits at the register budget); the item's
+            // coordinates are recomputed for the epilogue
+            const bool has_b = two_tiles(item);
+            const bool is_last2 = item == last2;
+            if (t == 1 && !has_b) continue;
             float l = 0.0f;
             if constexpr (FAST) {
                 // ---- max-free pass: q arrives pre-scaled, so a score IS the base-2 exponent and p = 2^s needs no running
                 // maximum as long as the exponents stay inside what bf16 P and fp32 O / l can hold; rows that leave that
-                // range are detected on l afterwards and their CTA is redone by the safe kernel.  Per score: MUFU (or the
+                // range are detected on l afterwards and their item is redone by the safe kernel.  Per score: MUFU (or the
                 // FMA-pipe polynomial), half an FADD2 and half an F2FP -- no scale FMA, no max, no rescale logic.
                 float l_f = 0.0f;
-                const int bar_mine_f = 1 + q * 2 + t, bar_other_f = 1 + q * 2 + (t ^ 1);
-                if (PINGPONG && has_b && t == 1) named_arrive(bar_other_f, 64);   // tile A goes first
                 for (int j = 0; j < nfull; ++j) {
                     if (q == 0 && lane == 0) TRACE(t, j, 0);
-                    ptx::mbar_wait(&s_full[t], j & 1);
+                    ptx::mbar_wait_quiet(&s_full[t], (gt + j) & 1);
                     if (q == 0 && lane == 0) TRACE(t, j, 1);
                     ptx::tc_fence_after();
                     uint32_t s[4][32];
@@ -292,8 +349,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     ptx::tc_wait_ld();
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(&s_free[t]);          // the MMA warp may overwrite S with the next block's scores
-                    if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);   // P buffer free again (normally long since)
-                    if (PINGPONG && has_b) named_sync(bar_mine_f, 64);
+                    if (j > 0) ptx::mbar_wait_quiet(&pv_done[t], (gt + j - 1) & 1);   // P buffer free again (normally long since)
+                    if (PINGPONG && has_b) named_sync(bar_mine, 64);
                     if (q == 0 && lane == 0) TRACE(t, j, 2);
                     ptx::F2 sums[4] = {{0ull}, {0ull}, {0ull}, {0ull}};
 #pragma unroll
@@ -313,7 +370,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                             pk[i] = ptx::pack_bf16x2(p0, p1);
                         }
                         ptx::tmem_st16(t_p + ch * 16, pk);
-                        if (PINGPONG && ch == HANDOVER_CH && has_b && !(t == 1 && j == nkv - 1)) named_arrive(bar_other_f, 64);
+                        if (PINGPONG && ch == HANDOVER_CH && has_b && !(t == 1 && j == nkv - 1 && is_last2)) named_arrive(bar_other, 64);
                     }
                     float a0, a1, b0, b1;
                     ptx::f2_get(ptx::f2_add(sums[0], sums[1]), a0, a1);
@@ -326,10 +383,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                 }
                 if (tail > 0) {
                     const int j = nfull;
-                    ptx::mbar_wait(&s_full[t], j & 1);
+                    ptx::mbar_wait_quiet(&s_full[t], (gt + j) & 1);
                     ptx::tc_fence_after();
-                    if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);
-                    if (PINGPONG && has_b) named_sync(bar_mine_f, 64);
+                    if (j > 0) ptx::mbar_wait_quiet(&pv_done[t], (gt + j - 1) & 1);
+                    if (PINGPONG && has_b) named_sync(bar_mine, 64);
                     float sum = 0.0f;
                     for (int c0 = 0; c0 < tail_n; c0 += 16) {
                         uint32_t v[16], pk[8];
@@ -345,24 +402,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                         ptx::tmem_st8(t_p + (c0 >> 1), pk);
                     }
                     l_f += sum;
-                    if (PINGPONG && has_b && t == 0) named_arrive(bar_other_f, 64);
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&s_free[t]);          // keeps the barrier's phase count uniform (one per key block)
+                    if (PINGPONG && has_b && (t == 0 || !is_last2)) named_arrive(bar_other, 64);
                     ptx::tc_wait_st();
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(&p_ready[t]);
                 }
                 // 2^-100 < l < 2^100 bounds every p (and p * v) far away from fp32 overflow and from total underflow;
-                // anything else (inf, NaN, 0) sends the CTA to the safe pass.  Padding rows beyond `tokens` are ignored.
-                const bool row_live = q0 + t * BQ + q * 32 + lane < p.tokens;
-                if (row_live && !(l_f > 7.888609052210118e-31f && l_f < 1.2676506002282294e30f)) p.flags[cta_id] = 1;
+                // anything else (inf, NaN, 0) sends the item to the safe pass.  Padding rows beyond `tokens` are ignored.
+                const bool row_live = (item % p.units) * 2 * BQ + t * BQ + q * 32 + lane < p.tokens;
+                if (row_live && !(l_f > 7.888609052210118e-31f && l_f < 1.2676506002282294e30f)) p.flags[item] = 1;
                 l = l_f;
             } else {
             const float c = p.scale_log2e;
             float m_used = -INFINITY;
-            // Ping-pong on the exponential (MUFU) pipe: warps 4+q (tile A) and 8+q (tile B) share an SM sub-partition.
-            // Left alone they run their exponentials at the same time (pipe oversubscribed) and their TMEM loads /
-            // row maxima at the same time (pipe idle); strict alternation keeps the pipe busy.
-            const int bar_mine = 1 + q * 2 + t, bar_other = 1 + q * 2 + (t ^ 1);
-            if (PINGPONG && has_b && t == 1) named_arrive(bar_other, 64);   // tile A goes first
             // lazy running-max update: O and l are rescaled only when the row max grew by more than 2^8
             auto raise_max = [&](float m_blk, int j) {
                 const bool grow = m_blk > m_used + RESCALE_THRESHOLD;
@@ -370,7 +424,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     const float m_new = grow ? m_blk : m_used;
                     const float f = ptx::ex2_approx(m_used - m_new);  // 0 on the first block, 1 if unchanged
                     if (j > 0) {
-                        ptx::mbar_wait(&pv_done[t], (j - 1) & 1);     // P V of block j-1 has landed in O
+                        ptx::mbar_wait_quiet(&pv_done[t], (gt + j - 1) & 1);     // P V of block j-1 has landed in O
                         ptx::tc_fence_after();
                         uint32_t o[32];
 #pragma unroll
@@ -389,7 +443,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             // ---- full 128-key blocks: no masking anywhere on this path ----
             for (int j = 0; j < nfull; ++j) {
                 if (q == 0 && lane == 0) TRACE(t, j, 0);
-                ptx::mbar_wait(&s_full[t], j & 1);
+                ptx::mbar_wait_quiet(&s_full[t], (gt + j) & 1);
                 if (q == 0 && lane == 0) TRACE(t, j, 1);
                 ptx::tc_fence_after();
                 uint32_t s[4][32];
@@ -410,7 +464,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     mx[a] = fmaxf(mx[a], __uint_as_float(sv[15]));
                 }
                 raise_max(max3(max3(mx[0], mx[1], mx[2]), max3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * c, j);
-                if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);   // P buffer free again (normally long since)
+                if (j > 0) ptx::mbar_wait_quiet(&pv_done[t], (gt + j - 1) & 1);   // P buffer free again (normally long since)
                 if (PINGPONG && has_b) named_sync(bar_mine, 64);       // my turn on the exponential pipe
                 if (q == 0 && lane == 0) TRACE(t, j, 2);
                 const float nm = -m_used;
@@ -434,7 +488,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     }
                     ptx::tmem_st16(t_p + ch * 16, pk);
                     // hand the exponential pipe to the other tile's warp a little before my last chunk drains
-                    if (PINGPONG && ch == HANDOVER_CH && has_b && !(t == 1 && j == nkv - 1)) named_arrive(bar_other, 64);
+                    if (PINGPONG && ch == HANDOVER_CH && has_b && !(t == 1 && j == nkv - 1 && is_last2)) named_arrive(bar_other, 64);
                 }
                 {
                     float a0, a1, b0, b1;
@@ -450,7 +504,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             // ---- tail block: tail (< 128) valid keys in tail_n = ceil16(tail) score columns; the only masked path ----
             if (tail > 0) {
                 const int j = nfull;
-                ptx::mbar_wait(&s_full[t], j & 1);
+                ptx::mbar_wait_quiet(&s_full[t], (gt + j) & 1);
                 ptx::tc_fence_after();
                 float mx = -INFINITY;
                 for (int c0 = 0; c0 < tail_n; c0 += 16) {
@@ -462,7 +516,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                         if (c0 + i < tail) mx = fmaxf(mx, __uint_as_float(v[i]));
                 }
                 raise_max(mx * c, j);
-                if (j > 0) ptx::mbar_wait(&pv_done[t], (j - 1) & 1);
+                if (j > 0) ptx::mbar_wait_quiet(&pv_done[t], (gt + j - 1) & 1);
                 if (PINGPONG && has_b) named_sync(bar_mine, 64);
                 const float nm = -m_used;
                 float sum = 0.0f;
@@ -480,40 +534,50 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                     ptx::tmem_st8(t_p + (c0 >> 1), pk);
                 }
                 l += sum;
-                if (PINGPONG && has_b && t == 0) named_arrive(bar_other, 64);   // tile B's tail block; nobody follows B
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&s_free[t]);          // keeps the barrier's phase count uniform (one per key block)
+                if (PINGPONG && has_b && (t == 0 || !is_last2)) named_arrive(bar_other, 64);
                 ptx::tc_wait_st();
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&p_ready[t]);
             }
             }
             // ---- output: O / l -> bf16, token-major (B*tokens, D) at column head*64 ----
-            ptx::mbar_wait(&pv_done[t], (nkv - 1) & 1);   // the last P V has landed in O
+            ptx::mbar_wait_quiet(&pv_done[t], (gt + nkv - 1) & 1);   // the last P V has landed in O
             ptx::tc_fence_after();
-            const int row = q0 + t * BQ + q * 32 + lane;
+            uint32_t o[2][32];
+            ptx::tmem_ld32(t_o, o[0]);
+            ptx::tmem_ld32(t_o + 32, o[1]);
+            ptx::tc_wait_ld();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&o_free[t]);                      // the next item's first P V may overwrite O
+            gt += nkv;
+            const int unit = item % p.units, head = (item / p.units) % p.heads, img = item / (p.units * p.heads);
+            const int row = unit * 2 * BQ + t * BQ + q * 32 + lane;
             const float inv = 1.0f / l;
-            __nv_bfloat16* dst = p.out + (static_cast<size_t>(img) * p.tokens + row) * p.D + head * HD;
+            if (row < p.tokens) {
+                __nv_bfloat16* dst = p.out + (static_cast<size_t>(img) * p.tokens + row) * p.D + head * HD;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t o[32];
-                ptx::tmem_ld32(t_o + h * 32, o);
-                ptx::tc_wait_ld();
-                if (row < p.tokens) {
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         uint4 pkt;
-                        pkt.x = ptx::pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-                        pkt.y = ptx::pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-                        pkt.z = ptx::pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-                        pkt.w = ptx::pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                        pkt.x = ptx::pack_bf16x2(__uint_as_float(o[h][8 * i + 0]) * inv, __uint_as_float(o[h][8 * i + 1]) * inv);
+                        pkt.y = ptx::pack_bf16x2(__uint_as_float(o[h][8 * i + 2]) * inv, __uint_as_float(o[h][8 * i + 3]) * inv);
+                        pkt.z = ptx::pack_bf16x2(__uint_as_float(o[h][8 * i + 4]) * inv, __uint_as_float(o[h][8 * i + 5]) * inv);
+                        pkt.w = ptx::pack_bf16x2(__uint_as_float(o[h][8 * i + 6]) * inv, __uint_as_float(o[h][8 * i + 7]) * inv);
                         reinterpret_cast<uint4*>(dst + h * 32)[i] = pkt;
                     }
-                }
             }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (warp == 2) {
+        ROLE_LOCALS;
+        ptx::tmem_dealloc<TMEM_COLS>(*tmem_slot);
+    }
+#undef ROLE_LOCALS
 }
 
 }  // namespace
@@ -541,8 +605,9 @@ int attention_launch(const void* qk, const void* vt, void* out, int B, int token
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
         configured = true;
     }
-    AttnParams p{static_cast<__nv_bfloat16*>(out), tokens, heads, D, scale, flags};
-    dim3 grid(ceil_div(tokens, 2 * BQ), heads, B);
+    const int units = ceil_div(tokens, 2 * BQ);
+    AttnParams p{static_cast<__nv_bfloat16*>(out), tokens, heads, D, scale, flags, units * heads * B, units};
+    const int grid = p.n_items < vittf_num_sms() ? p.n_items : vittf_num_sms();
     if (fast) attention_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm_qk, tm_vt, p);
     else attention_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm_qk, tm_vt, p);
     VITTF_CHECK_CUDA(cudaGetLastError());

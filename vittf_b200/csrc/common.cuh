@@ -110,6 +110,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+// Same bound without the report: the printf call and its argument staging cost registers in every inlined wait, which
+// the 64-register issuer roles of the attention kernel cannot afford (they spilled into their MMA issue loop).
+__device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
 
 // ---- TMA (cp.async.bulk.tensor) ---------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
