@@ -31,9 +31,9 @@ sys.path.insert(0, str(ROOT))
 WORKLOADS = {
     # name: (volume size, arch, fos, classes, annotations per class, batch)
     "tiny": (32, "vits8", 8, 4, 2, 8),
-    "cfg1": (128, "vits8", 64, 4, 8, 32),
-    "cfg2": (256, "vits8", 64, 8, 4, 32),
-    "cfg3": (512, "vitb8", 64, 16, 2, 16),
+    "cfg1": (128, "vits8", 64, 4, 8, 64),
+    "cfg2": (256, "vits8", 64, 8, 4, 64),
+    "cfg3": (512, "vitb8", 64, 16, 2, 64),
 }
 WORKLOAD_TEXT = {
     "tiny": "smoke: 32^3 uint8 phantom, ViT-S/8 random init, 64^2 images, 4 classes",
@@ -143,6 +143,8 @@ def cpu_reference(workload, budget_s=20.0):
 
 # --------------------------------------------------------------------------------------------- main
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner to stdout: rank 0 must print ONE JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -281,10 +283,10 @@ def main():
     gemm_ms, gemm_n = timing["gemm"]
     n_img = 3 * size
     total_flops = needed_flops_per_image(arch, tokens) * n_img
-    # DRAM bytes of one attention launch from the committed `ncu --set full` capture (profiles/r1_ncu_attention_v5.json:
-    # dram__bytes_read.sum + dram__bytes_write.sum = 305.4 + 84.4 MB at ViT-S/8, 32 slices of 4097 tokens); the algorithmic
-    # bytes of that launch (q, k, V^T read once, output written once) are 4 * B * tokens * D * 2 = 403 MB
-    traffic = 389.78e6 if (arch == "vits8" and batch == 32 and tokens == 4097) else None
+    # DRAM bytes of one attention launch from the committed `ncu --set full` capture (profiles/r1_ncu_attention_v7.json:
+    # dram__bytes_read.sum + dram__bytes_write.sum = 610.4 + 182.7 MB at ViT-S/8, 64 slices of 4097 tokens); the algorithmic
+    # bytes of that launch (q, k, V^T read once, output written once) are 4 * B * tokens * D * 2 = 805 MB
+    traffic = 793.1e6 if (arch == "vits8" and batch == 64 and tokens == 4097 and world == 1) else None
     out = {
         "metric": "ms per volume end-to-end (ViT feats + similarity)", "value": ms_dev, "unit": "ms", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": False,
@@ -295,7 +297,7 @@ def main():
         "roofline": {"kernel": "attention_kernel (tcgen05 flash attention, hd 64)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
                      "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
-                     "traffic_source": "profiles/r1_ncu_attention_v5.json" if traffic else None, "peak_source": peak_src, "avg_launch_ms": att_avg_ms, "launches_timed": int(att_n),
+                     "traffic_source": "profiles/r1_ncu_attention_v7.json" if traffic else None, "peak_source": peak_src, "avg_launch_ms": att_avg_ms, "launches_timed": int(att_n),
                      "share_of_step": att_ms / (ms_dev * args.steps) if ms_dev else None,
                      "gemm_share_of_step": gemm_ms / (ms_dev * args.steps) if ms_dev else None},
         "vit_tflops_needed": total_flops / world / (ms_dev * 1e-3) / 1e12 * world,

@@ -14,7 +14,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for D in (384, 768):
     M = B * tokens
     for name, N, K, epi in (("qkv", 3 * D, D, _lib.EPI_QKV_SPLIT), ("proj", D, D, _lib.EPI_BIAS_RESID_F32),
-                            ("fc1", 4 * D, D, _lib.EPI_BIAS_GELU_BF16), ("fc2", D, 4 * D, _lib.EPI_BIAS_RESID_F32)):
+                            ("fc1", 4 * D, D, _lib.EPI_BIAS_GELU_BF16), ("fc1 without GELU", 4 * D, D, _lib.EPI_BIAS_BF16),
+                            ("fc2", D, 4 * D, _lib.EPI_BIAS_RESID_F32)):
         a = torch.randn(M, K, device="cuda").bfloat16()
         w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
         bias = torch.zeros(N, device="cuda")

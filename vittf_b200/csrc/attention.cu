@@ -107,7 +107,7 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
 #define POLY_EVERY_V 4     // measured on B200: 4 (25 %) > 0 > 2
 #endif
 #ifndef HANDOVER_CH
-#define HANDOVER_CH 2      // hand the pipe over after 3 of the 4 column chunks
+#define HANDOVER_CH 3      // hand the pipe over after the last column chunk (measured: 3 >= 0 ~ 1 ~ 2 with persistent CTAs)
 #endif
 #ifndef POLY_NUM
 #define POLY_NUM 1         // POLY_NUM of every POLY_EVERY_V pairs of exponentials run on the FMA pipe (0 = none)
@@ -163,6 +163,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     (void)s_q; (void)q_full; (void)q_empty; (void)kv_full; (void)kv_empty; (void)s_full; (void)s_free; (void)p_ready;     \
     (void)pv_done; (void)o_free; (void)tmem_slot; (void)tail_n; (void)nkv; (void)visit; (void)two_tiles
 
+    if (!FAST && p.flags != nullptr) {
+        // second pass: leave at once unless one of this CTA's items was flagged (all threads scan in parallel; walking the
+        // items role by role costs a dependent global load per item -- 24 us for nothing in the common case)
+        int any = 0;
+        for (int item = blockIdx.x + threadIdx.x * gridDim.x; item < p.n_items; item += blockDim.x * gridDim.x) any |= p.flags[item];
+        if (!__syncthreads_or(any)) return;
+    }
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
     const int lane = threadIdx.x & 31;
     {
