@@ -144,6 +144,91 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(PatchParams q) {
     }
 }
 
+// Register-tiled variant for patch 8 (the benchmark backbones): the folded (64 taps x 384 d) weight panel stays in
+// shared memory while a persistent CTA walks (image, patch row) items; per item the 64 taps of up to 64 patches are
+// gathered once, and every thread accumulates 8 patches x 12 channels (96 FMAs per 2 broadcast LDS.128 + 12 LDS.32).
+// The generic kernel above issued one LDS and one LDG per FMA and was 5 % of the ViT step.
+constexpr int PE_TAPS = 64, PE_DCH = 384, PE_PX = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256) patch_embed_tiled_kernel(PatchParams q, int n_items) {
+    extern __shared__ float s_pe[];
+    float* s_w = s_pe;                          // [64 taps][384 d]
+    float* s_g = s_pe + PE_TAPS * PE_DCH;       // [64 taps][64 px]
+    const int d0 = blockIdx.y * PE_DCH;         // channel chunk of this CTA
+    for (int i = threadIdx.x; i < PE_TAPS * PE_DCH; i += 256) {
+        const int t = i / PE_DCH, d = i - t * PE_DCH;
+        s_w[i] = q.w[static_cast<size_t>(t) * q.D + d0 + d];
+    }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int ntok = 1 + q.f0 * q.f1;
+    const float lo = q.minmax[0], inv = 1.0f / (q.minmax[1] - q.minmax[0]);
+    const float sc0 = static_cast<float>(q.a) / static_cast<float>(q.im0);
+    const float sc1 = static_cast<float>(q.b) / static_cast<float>(q.im1);
+    const T* vol = static_cast<const T*>(q.vol);
+    float bias[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) bias[k] = q.bias[d0 + tx + 32 * k];
+    const int rows_per_img = q.f0 + 1;          // patch rows + one CLS item
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int img = item / rows_per_img, py = item - img * rows_per_img;
+        float* out_img = q.out + static_cast<size_t>(img) * ntok * q.D;
+        if (py == q.f0) {                       // CLS token: cls + pos[0]
+            for (int d = threadIdx.x; d < PE_DCH; d += 256) out_img[d0 + d] = q.pos[d0 + d];
+            continue;
+        }
+        const int s = q.s0 + img;
+        for (int px0 = 0; px0 < q.f1; px0 += PE_PX) {
+            __syncthreads();                    // previous gather fully consumed (and the weight panel is in place)
+            for (int i = threadIdx.x; i < PE_TAPS * PE_PX; i += 256) {
+                const int t = i >> 6, px = i & 63;          // consecutive threads: consecutive patches (conflict-free stores)
+                const int u = t >> 3, v = t & 7;
+                float val = 0.0f;
+                if (px0 + px < q.f1) {
+                    const int r = nearest_src(py * 8 + u, q.a, q.im0, sc0);
+                    const int c = nearest_src((px0 + px) * 8 + v, q.b, q.im1, sc1);
+                    int64_t idx;
+                    if (q.axis == 2) idx = (static_cast<int64_t>(r) * q.Y + c) * q.Z + s;        // rows X, cols Y
+                    else if (q.axis == 1) idx = (static_cast<int64_t>(r) * q.Y + s) * q.Z + c;   // rows X, cols Z
+                    else idx = (static_cast<int64_t>(s) * q.Y + r) * q.Z + c;                    // rows Y, cols Z
+                    val = (load_as_float<T>(vol, idx) - lo) * inv;
+                }
+                s_g[t * PE_PX + px] = val;
+            }
+            __syncthreads();
+            float acc[8][12];
+            const int tok0 = 1 + py * q.f1 + px0 + ty * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool live = px0 + ty * 8 + j < q.f1;
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                    acc[j][k] = bias[k] + (live ? __ldg(q.pos + static_cast<size_t>(tok0 + j) * q.D + d0 + tx + 32 * k) : 0.0f);
+            }
+#pragma unroll 4
+            for (int t = 0; t < PE_TAPS; ++t) {
+                const float4 g0 = *reinterpret_cast<const float4*>(s_g + t * PE_PX + ty * 8);       // warp-wide broadcast
+                const float4 g1 = *reinterpret_cast<const float4*>(s_g + t * PE_PX + ty * 8 + 4);
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                float w[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) w[k] = s_w[t * PE_DCH + tx + 32 * k];                 // conflict-free
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) acc[j][k] = fmaf(g[j], w[k], acc[j][k]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (px0 + ty * 8 + j >= q.f1) continue;
+                float* dst = out_img + static_cast<size_t>(tok0 + j) * q.D + d0 + tx;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) dst[32 * k] = acc[j][k];                              // 128 B per warp store
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LayerNorm (eps 1e-6) fp32 -> bf16, one warp per row, row held in registers.
 // ---------------------------------------------------------------------------------------------
@@ -315,10 +400,35 @@ extern "C" int vittf_patch_embed(const void* vol, int vol_dtype, int X, int Y, i
     q.b = axis == 2 ? Y : Z;
     q.im0 = im0; q.im1 = im1; q.p = patch; q.D = D; q.f0 = im0 / patch; q.f1 = im1 / patch;
     q.minmax = minmax2; q.w = patch_w; q.bias = patch_b; q.pos = pos_embed; q.out = out_tokens;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (patch == 8 && D % PE_DCH == 0) {        // register-tiled persistent kernel (patch-8 backbones)
+        const size_t smem_t = static_cast<size_t>(PE_TAPS) * (PE_DCH + PE_PX) * sizeof(float);
+        const int n_items = (s1 - s0) * (q.f0 + 1);
+        dim3 grid_t(n_items < vittf_num_sms() ? n_items : vittf_num_sms(), D / PE_DCH);
+#define LAUNCH_PET(T)                                                                                                   \
+    do {                                                                                                                \
+        static bool configured = false;                                                                                 \
+        if (!configured) {                                                                                              \
+            VITTF_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  static_cast<int>(smem_t)));                                          \
+            configured = true;                                                                                          \
+        }                                                                                                               \
+        patch_embed_tiled_kernel<T><<<grid_t, 256, smem_t, s>>>(q, n_items);                                            \
+    } while (0)
+        switch (vol_dtype) {
+            case VITTF_U8: LAUNCH_PET(uint8_t); break;
+            case VITTF_F16: LAUNCH_PET(__half); break;
+            case VITTF_F32: LAUNCH_PET(float); break;
+            default: VITTF_REQUIRE(false, "vittf_patch_embed: unsupported volume dtype %d", vol_dtype);
+        }
+#undef LAUNCH_PET
+        VITTF_CHECK_CUDA(cudaGetLastError());
+        vittf_count_launches(1);
+        return VITTF_OK;
+    }
     const size_t smem = static_cast<size_t>(q.f1) * patch * patch * sizeof(float);
     VITTF_REQUIRE(smem <= 200 * 1024, "vittf_patch_embed: image row too wide (%zu B of shared memory)", smem);
     dim3 grid(q.f0 + 1, s1 - s0);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define LAUNCH_PE(T)                                                                                          \
     do {                                                                                                      \
         if (smem > 48 * 1024)                                                                                 \
