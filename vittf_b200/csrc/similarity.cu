@@ -327,7 +327,9 @@ __global__ void __launch_bounds__(128) sim_lowres_tma_kernel(const __grid_consta
         for (int c = 0; c < LF_STAGES && c < nchunk; ++c) issue(c);
     }
     // prototype panel, transposed to [f][a]: coalesced 16-byte loads along f, all in flight at once
-    if ((F & 3) == 0 && (reinterpret_cast<uintptr_t>(protos) & 15) == 0) {
+    if constexpr (AT == 0) {
+        // Gram planes only (the dots run on the tensor cores, sim_dots_mma_kernel)
+    } else if ((F & 3) == 0 && (reinterpret_cast<uintptr_t>(protos) & 15) == 0) {
         const int f4n = F >> 2;
 #pragma unroll 4
         for (int i = tid; i < f4n * AT; i += 128) {
@@ -345,12 +347,13 @@ __global__ void __launch_bounds__(128) sim_lowres_tma_kernel(const __grid_consta
     }
     __syncthreads();
 
-    ptx::F2 acc[4][AT / 2];
+    constexpr int AH = AT > 0 ? AT / 2 : 1;
+    ptx::F2 acc[4][AH];
     float g[4][14];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
 #pragma unroll
-        for (int i = 0; i < AT / 2; ++i) acc[v][i].v = 0ull;
+        for (int i = 0; i < AH; ++i) acc[v][i].v = 0ull;
 #pragma unroll
         for (int o = 0; o < 14; ++o) g[v][o] = 0.0f;
     }
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(128) sim_lowres_tma_kernel(const __grid_consta
             }
             const float* pf = s_p + static_cast<size_t>(c * LF_FS + ff) * AT;
 #pragma unroll
-            for (int i = 0; i < AT / 2; i += 2) {
+            for (int i = 0; i < AT / 2; i += 2) {       // (no iterations when AT == 0)
                 const float4 pv = *reinterpret_cast<const float4*>(pf + 2 * i);     // broadcast: same address in every lane
                 const ptx::F2 p01 = ptx::f2_make(pv.x, pv.y), p23 = ptx::f2_make(pv.z, pv.w);
 #pragma unroll
@@ -460,6 +463,157 @@ int launch_lowres_tma_one(const CUtensorMap& tm, int F, int w, int h, int d, con
     return VITTF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// pass 1, prototype dots on the tensor cores (fp16 feature volumes): dots[a][v] = sum_f feats[f][v] * protos[a][f] is a
+// (n_lr x F) x (F x A) GEMM whose A operand is stored "voxel-major" -- exactly what ldmatrix.trans delivers.  Warp-level
+// mma.sync (m16n8k16, fp32 accumulate) is ample here: the kernel only has to keep up with the feature stream from HBM
+// (F * n_lr * 2 bytes), which the FMA pipe could not (it bounded the dots at ~130 us for 32 prototypes at 64^3).
+// One CTA = 128 consecutive voxels (4 warps x 32); feature planes arrive as 128B-swizzled TMA boxes of 64 voxels x 32 f;
+// the prototypes (rounded to fp16, unit vectors: 3e-5 on a dot) sit in shared memory, rows padded against bank conflicts.
+// ---------------------------------------------------------------------------------------------
+constexpr int DM_BM = 128, DM_BK = 32, DM_STAGES = 4;
+constexpr int DM_STAGE_BYTES = 2 * DM_BK * 128;           // two boxes of (32 f) x (64 voxels x 2 B)
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NT>   // N-tiles of 8 prototypes handled by the CTA (A <= 8 * NT)
+__global__ void __launch_bounds__(128) sim_dots_mma_kernel(const __grid_constant__ CUtensorMap tm_f, int F, int64_t n,
+                                                           const float* __restrict__ protos, int A, int a_base,
+                                                           float* __restrict__ dots) {
+    extern __shared__ __align__(1024) uint8_t dm_smem_raw[];
+    uint8_t* dm_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dm_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_t = dm_smem;                                                   // [stage][box][32 f][64 v] halves, swizzled
+    __half* s_p = reinterpret_cast<__half*>(dm_smem + DM_STAGES * DM_STAGE_BYTES);   // [8 NT][F + 8]
+    const int pstride = F + 8;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_p + static_cast<size_t>(8 * NT) * pstride);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t v0 = static_cast<int64_t>(blockIdx.x) * DM_BM;
+    const int nchunk = (F + DM_BK - 1) / DM_BK;
+    if (tid == 0) {
+        for (int i = 0; i < DM_STAGES; ++i) ptx::mbar_init(&full[i], 1);
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int c) {
+        uint64_t* bar = &full[c % DM_STAGES];
+        uint8_t* dst = s_t + (c % DM_STAGES) * DM_STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(bar, DM_STAGE_BYTES);
+        ptx::tma_load_2d(dst, &tm_f, bar, static_cast<int>(v0), c * DM_BK);
+        ptx::tma_load_2d(dst + DM_BK * 128, &tm_f, bar, static_cast<int>(v0) + 64, c * DM_BK);
+    };
+    if (tid == 0) {
+        ptx::prefetch_tmap(&tm_f);
+        for (int c = 0; c < DM_STAGES && c < nchunk; ++c) issue(c);
+    }
+    for (int i = tid; i < 8 * NT * pstride; i += 128) {
+        const int aa = i / pstride, ff = i - aa * pstride;
+        const int a = a_base + aa;
+        s_p[i] = __float2half_rn(a < A && ff < F ? protos[static_cast<size_t>(a) * F + ff] : 0.0f);
+    }
+    __syncthreads();
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.0f;
+    // ldmatrix row address of this lane inside a stage: matrix i = lane / 8, row r = lane % 8
+    const int mi = lane >> 3, mr = lane & 7;
+    const uint32_t p_base = ptx::smem_u32(s_p);
+    for (int c = 0; c < nchunk; ++c) {
+        ptx::mbar_wait(&full[c % DM_STAGES], (c / DM_STAGES) & 1);
+        const uint32_t st = ptx::smem_u32(s_t + (c % DM_STAGES) * DM_STAGE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < DM_BK / 16; ++ks) {
+            uint32_t af[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                // A fragment of voxels [wid*32 + m*16, +16): matrices (m0:8,k0:8) (m8:16,k0:8) (m0:8,k8:16) (m8:16,k8:16)
+                const int vloc = wid * 32 + m * 16 + (mi & 1) * 8;      // voxel offset inside the CTA tile
+                const int f = ks * 16 + (mi >> 1) * 8 + mr;              // feature row inside the stage
+                const int box = vloc >> 6, chunk = (vloc & 63) >> 3;
+                ldmatrix_x4_trans(st + box * (DM_BK * 128) + f * 128 + ((chunk ^ (f & 7)) << 4), af[m]);
+            }
+#pragma unroll
+            for (int j = 0; j < NT; j += 2) {
+                // B fragments of prototypes [8j, 8j+16): matrices (n0:8,k0:8) (n0:8,k8:16) (n8:16,k0:8) (n8:16,k8:16)
+                uint32_t bf[4];
+                const int prow = 8 * j + (mi >> 1) * 8 + mr;
+                const int pk = c * DM_BK + ks * 16 + (mi & 1) * 8;
+                if (j + 1 < NT || (NT & 1) == 0) {
+                    ldmatrix_x4(p_base + (prow * pstride + pk) * 2, bf);
+                } else {                                                 // odd tail: second tile does not exist
+                    ldmatrix_x4(p_base + ((8 * j + mr) * pstride + pk) * 2, bf);
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    mma_f16_16816(acc[m][j], af[m], bf[0], bf[1]);
+                    if (j + 1 < NT) mma_f16_16816(acc[m][j + 1], af[m], bf[2], bf[3]);
+                }
+            }
+        }
+        __syncthreads();                                   // every warp is done with this stage
+        if (tid == 0 && c + DM_STAGES < nchunk) issue(c + DM_STAGES);
+    }
+    // D fragment: d0,d1 -> (row lane/4, cols 2*(lane%4) + {0,1}); d2,d3 -> row + 8
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int a = a_base + 8 * j + 2 * (lane & 3) + (e & 1);
+                const int64_t v = v0 + wid * 32 + m * 16 + (lane >> 2) + (e >> 1) * 8;
+                if (a < A && v < n) dots[static_cast<size_t>(a) * n + v] = acc[m][j][e];
+            }
+}
+
+template <int NT>
+int launch_dots_mma_one(const CUtensorMap& tm, int F, int64_t n, const float* protos, int A, int a_base, float* dots,
+                        cudaStream_t s) {
+    const size_t smem = static_cast<size_t>(DM_STAGES) * DM_STAGE_BYTES + static_cast<size_t>(8 * NT) * (F + 8) * 2 + 64 + 1024;
+    auto kern = sim_dots_mma_kernel<NT>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+    }
+    kern<<<static_cast<unsigned>(ceil_div_ll(n, DM_BM)), 128, smem, s>>>(tm, F, n, protos, A, a_base, dots);
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
+
+// all prototypes, 64 per launch
+int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, int A, float* dots, cudaStream_t s) {
+    CUtensorMap tm;
+    const uint64_t dims[2] = {static_cast<uint64_t>(n), static_cast<uint64_t>(F)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(n) * 2};
+    const uint32_t box[2] = {64, DM_BK};
+    VITTF_CHECK(vittf_make_tmap(&tm, feats, 2, 2, dims, strides, box, true));
+    for (int a_base = 0; a_base < A; a_base += 64) {
+        const int rem = A - a_base;
+        int rc;
+        if (rem > 32) rc = launch_dots_mma_one<8>(tm, F, n, protos, A, a_base, dots, s);
+        else if (rem > 16) rc = launch_dots_mma_one<4>(tm, F, n, protos, A, a_base, dots, s);
+        else if (rem > 8) rc = launch_dots_mma_one<2>(tm, F, n, protos, A, a_base, dots, s);
+        else rc = launch_dots_mma_one<1>(tm, F, n, protos, A, a_base, dots, s);
+        VITTF_CHECK(rc);
+    }
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    return VITTF_OK;
+}
+
 // The Gram planes ride along with the first group of <= 16 prototypes (halo box); the remaining prototypes run in
 // groups of <= 32 on halo-free boxes.
 template <bool GRAM>
@@ -472,6 +626,18 @@ int launch_lowres_tma(const __half* feats, int F, int w, int h, int d, const flo
     VITTF_CHECK(vittf_make_tmap(&tm_halo, feats, 2, 4, dims, strides, box_halo, false));
     VITTF_CHECK(vittf_make_tmap(&tm_brick, feats, 2, 4, dims, strides, box_brick, false));
     int a_base = 0;
+    const int64_t n = static_cast<int64_t>(w) * h * d;
+    static const bool no_mma = getenv("VITTF_SIM_NO_MMA") != nullptr;     // A/B switch: FFMA2 dots
+    if (!no_mma && F % DM_BK == 0 && n % 8 == 0) {
+        // dots of all prototypes on the tensor cores; the Gram planes (the only part that needs the halo) on the FMA pipe
+        VITTF_CHECK(launch_dots_mma(feats, F, n, protos, A, dots, s));
+        if (GRAM) {
+            const int rc = launch_lowres_tma_one<0, true>(tm_halo, F, w, h, d, protos, A, 0, dots, gram, s);
+            VITTF_CHECK(rc);
+        }
+        VITTF_CHECK_CUDA(cudaGetLastError());
+        return VITTF_OK;
+    }
     if (GRAM) {
         const int rc = A > 8 ? launch_lowres_tma_one<16, true>(tm_halo, F, w, h, d, protos, A, 0, dots, gram, s)
                              : launch_lowres_tma_one<8, true>(tm_halo, F, w, h, d, protos, A, 0, dots, gram, s);
