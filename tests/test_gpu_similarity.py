@@ -80,15 +80,17 @@ def test_compute_similarities_with_bilateral_solver(golden):
 @pytest.mark.parametrize("lr,out_shape,F_,A", [((6, 5, 4), (24, 15, 20), 24, 6), ((16, 16, 16), (64, 64, 64), 96, 8),
                                                ((8, 8, 8), (8, 8, 8), 32, 3), ((12, 10, 8), (31, 29, 17), 40, 20),
                                                ((8, 8, 8), (16, 16, 16), 32, 5), ((8, 8, 8), (64, 64, 64), 48, 9),
-                                               ((33, 33, 33), (132, 132, 132), 16, 4)])
+                                               ((33, 33, 33), (132, 132, 132), 16, 4), ((6, 5, 4), (24, 20, 16), 24, 7),
+                                               ((5, 4, 6), (40, 32, 48), 32, 12), ((32, 32, 32), (128, 128, 128), 64, 32)])
 def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
     from oracle import similarity as osim, synth
     from vittf_b200.similarity import similarity_maps
     C = min(A, 3)
     feats, protos = synth.class_features(F_, lr, C, seed=2, dtype=torch.float16)
     g = torch.Generator().manual_seed(9)
-    p = F.normalize(protos.repeat((A + C - 1) // C, 1)[:A] + 0.05 * torch.randn(A, F_, generator=g), dim=-1)
     offs = [round(i * A / C) for i in range(C + 1)]
+    owner = torch.tensor([c for c in range(C) for _ in range(offs[c + 1] - offs[c])])     # prototype -> its class
+    p = F.normalize(protos[owner] + 0.05 * torch.randn(A, F_, generator=g), dim=-1)
     ref = osim.ns_composite(feats, p, offs, out_shape, exponent=2.0, slab=5)
     out = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
                           out_shape, mode="ns", exponent=2.0).cpu()
@@ -98,6 +100,11 @@ def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
     zs = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
                          out_shape, mode="ns", exponent=2.0, z_range=(3, out_shape[2] - 2)).cpu()
     assert torch.equal(zs, out[..., 3:out_shape[2] - 2])
+    if out_shape[2] >= 16:                                        # even slab bounds: the vectorised store path
+        zs = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
+                             out_shape, mode="ns", exponent=2.5, z_range=(4, out_shape[2] - 6)).cpu()
+        ref25 = osim.ns_composite(feats, p, offs, out_shape, exponent=2.5, slab=5)
+        assert (zs - ref25[..., 4:out_shape[2] - 6]).abs().max().item() < TOL
     # labels: >= 99.9 % agreement, exact where the top-2 margin exceeds 1e-2
     from vittf_b200.predict_ntf import argmax_labels
     lab = argmax_labels(out.cuda()).cpu().long()

@@ -990,6 +990,358 @@ void launch_cells(const UpParams& q, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// pass 2 on the tensor cores (NS mode, U in {4, 8}).  Inside a low-res cell the U^3 outputs of one prototype are
+//   out[o] = sum_{corner c} W[o][c] * dots[corner c],      W[o][c] = wx * wy * wz  -- the SAME U^3 x 8 matrix for every cell
+// (border cells clamp their corner INDICES, not their weights), so a tile of 16 cells is the GEMM
+//   D (16 cells x 64 outputs) = Corners (16 x 8) * W^T (8 x 64)
+// per prototype.  fp32 accuracy on bf16 tensor cores: corners split hi + mid (16 mantissa bits), weights split hi + lo
+// (they have up to 12 significant bits, bf16 keeps 8) -> [hi | hi] x [W_hi | W_lo] + [mid | mid] x [W_hi | W_lo]: two m16n8k16 per 16 x 8 tile,
+// relative error <= 2^-16.  The class max is a running FMNMX over the accumulator fragments (cells = rows, so no shuffles),
+// 1 / |interp(f)| comes from the Gram planes on the FMA pipe once per tile (amortised over all prototypes), outputs leave
+// as float2 along z.  A warp owns 16 consecutive cells of the flattened (cy, cz) cell grid at one cx -- the half cells
+// at the borders are ordinary rows, so no lane idles.  Instruction count per output voxel: ~90 (cell kernel: ~350).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+
+__device__ __forceinline__ const float* up_ptr_at(const float* base, uint32_t off) {      // one IMAD.WIDE.U32
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(off), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<const float*>(r);
+}
+
+// B fragment words of W^T for output (kx, ky, kz) and the corner pair k = (2t, 2t+1) = (bx = t>>1, by = t&1, bz = 0/1)
+template <int U>
+__device__ __forceinline__ uint2 up_w_frag(int kx, int ky, int kz, int t) {
+    const float tx = (kx + 0.5f) / U, ty = (ky + 0.5f) / U, tz = (kz + 0.5f) / U;
+    const float wxy = ((t >> 1) ? tx : 1.0f - tx) * ((t & 1) ? ty : 1.0f - ty);
+    const float w0 = wxy * (1.0f - tz), w1 = wxy * tz;                    // exact: <= 12 significant bits
+    const uint32_t hi = ptx::pack_bf16x2(w0, w1);
+    const uint32_t lo = ptx::pack_bf16x2(w0 - bf16_lo_f(hi), w1 - bf16_hi_f(hi));
+    return make_uint2(hi, lo);
+}
+
+__device__ __forceinline__ float rsqrt_fast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float* up_out_at(float* base, int off) {                         // one IMAD.WIDE
+    uint64_t r;
+    asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(r) : "r"(off), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<float*>(r);
+}
+// bits [lo, hi) of an 8-bit mask
+__device__ __forceinline__ uint32_t bit_range(int lo, int hi) {
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > 8 ? 8 : hi;
+    return hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+}
+
+constexpr int UP_PD = 4;            // prefetch distance of the corner dots, in prototypes
+
+template <int U, int EXPK>
+__global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, int cz_lo, int ncz, int tiles_per_x, int total_tasks) {
+    constexpr int NSUB = U == 8 ? 8 : 1;             // sub-blocks of 64 outputs per cell
+    extern __shared__ __align__(16) uint8_t um_smem[];
+    int* s_off = reinterpret_cast<int*>(um_smem);
+    uint2* s_w = reinterpret_cast<uint2*>(um_smem + (((q.C + 1) * 4 + 15) & ~15));   // [sub][ntile][lane]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i <= q.C; i += 128) s_off[i] = q.class_offsets[i];
+#pragma unroll 1
+    for (int i = threadIdx.x; i < NSUB * 8 * 32; i += 128) {
+        const int l = i & 31, sj = i >> 5;
+        if (U == 8) s_w[i] = up_w_frag<U>(sj >> 3, sj & 7, l >> 2, l & 3);
+        else s_w[i] = up_w_frag<U>(sj >> 1, 2 * (sj & 1) + (l >> 4), (l >> 2) & 3, l & 3);
+    }
+    __syncthreads();
+    const int task = static_cast<int>(blockIdx.x) * 4 + warp;
+    if (task >= total_tasks) return;
+    const int cxi = task / tiles_per_x, tile = task - cxi * tiles_per_x;
+    const int cx = cxi - 1;
+    const int w = q.w, h = q.h, d = q.d;
+    const int ncells = (h + 1) * ncz;
+    const uint32_t n_lr = static_cast<uint32_t>(w) * h * d;
+    const int zs = q.z1 - q.z0;
+    const int x0c = cx < 0 ? 0 : cx, x1c = cx + 1 > w - 1 ? w - 1 : cx + 1;
+    const int oxb = U * cx + U / 2;
+
+    // ---- the two cells (rows g, g + 8) of this thread -------------------------------------------------------
+    uint32_t off[2][2];              // A-fragment corner offsets: (row, bz)
+    int obase[2];                    // output offset of (kx, ky, kz) = (0, 0, 0) + the thread's fixed (ky, kz) part
+    float inv[2][8][2];
+    float Q[2][2][10];               // z-contracted Gram per row and per kz of the thread: (a, b) pairs of (bx, by) corners
+    const int kz0 = U == 4 ? 2 * (t & 1) : 2 * t;
+    const int ky_t = U == 4 ? (t >> 1) : 0;          // thread's fixed part of ky (U == 4: ky = 2 (j & 1) + (t >> 1))
+    bool zok[2][2];
+    int oyb[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int id = tile * 16 + g + 8 * r;
+        const bool rlive = id < ncells;
+        id = rlive ? id : ncells - 1;
+        const int cyi = id / ncz;
+        const int cy = cyi - 1, cz = cz_lo + (id - cyi * ncz);
+        const int y0c = cy < 0 ? 0 : cy, y1c = cy + 1 > h - 1 ? h - 1 : cy + 1;
+        const int z0c = cz < 0 ? 0 : cz, z1c = cz + 1 > d - 1 ? d - 1 : cz + 1;
+        const uint32_t line = (static_cast<uint32_t>((t >> 1) ? x1c : x0c) * h + ((t & 1) ? y1c : y0c)) * d;
+        off[r][0] = line + z0c;
+        off[r][1] = line + z1c;
+        const int oz = U * cz + U / 2 + kz0;
+        zok[r][0] = rlive && oz >= q.z0 && oz < q.z1 && oz >= 0 && oz < q.D;
+        zok[r][1] = rlive && oz + 1 >= q.z0 && oz + 1 < q.z1 && oz + 1 >= 0 && oz + 1 < q.D;
+        oyb[r] = U * cy + U / 2 + ky_t;
+        obase[r] = (oxb * q.H + oyb[r]) * zs + (oz - q.z0);
+        // Gram of the 8 corners -> contract z for the thread's two kz.  Distinct corners differ by exactly the cell's
+        // clamped extents (ex, ey, ez in {0, 1}); the slot of a pair is looked up from those.
+        const int ex = x1c - x0c, ey = y1c - y0c, ez = z1c - z0c;
+        const uint32_t base = (static_cast<uint32_t>(x0c) * h + y0c) * d + z0c;
+        const uint32_t sx = ex ? static_cast<uint32_t>(h) * d : 0u, sy = ey ? static_cast<uint32_t>(d) : 0u, sz = ez ? 1u : 0u;
+        float G[8][8];
+        const float* gb = q.gram + base;
+        if (ex & ey & ez) {
+            // interior cell: slots and anchor corners are compile-time, plane and corner offsets warp-uniform
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = a; b < 8; ++b) {
+                    bool swap;
+                    const int slot = gram_slot((b >> 2) - (a >> 2), ((b >> 1) & 1) - ((a >> 1) & 1), (b & 1) - (a & 1), swap);
+                    const int an = swap ? b : a;
+                    const size_t uo = static_cast<size_t>(slot) * n_lr + static_cast<size_t>(an >> 2) * (static_cast<uint32_t>(h) * d) +
+                                      static_cast<size_t>((an >> 1) & 1) * static_cast<uint32_t>(d) + (an & 1);
+                    const float gv = __ldg(gb + uo);
+                    G[a][b] = gv;
+                    G[b][a] = gv;
+                }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = a; b < 8; ++b) {
+                    bool swap;
+                    const int slot = gram_slot(((b >> 2) - (a >> 2)) * ex, (((b >> 1) & 1) - ((a >> 1) & 1)) * ey, ((b & 1) - (a & 1)) * ez, swap);
+                    const int an = swap ? b : a;        // anchor corner
+                    const uint32_t idx = ((an >> 2) ? sx : 0u) + (((an >> 1) & 1) ? sy : 0u) + ((an & 1) ? sz : 0u);
+                    const float gv = __ldg(gb + static_cast<size_t>(slot) * n_lr + idx);
+                    G[a][b] = gv;
+                    G[b][a] = gv;
+                }
+        }
+#pragma unroll
+        for (int zi = 0; zi < 2; ++zi) {
+            const float tz = (kz0 + zi + 0.5f) / U;
+            const float w00 = (1.0f - tz) * (1.0f - tz), w01 = (1.0f - tz) * tz, w11 = tz * tz;
+            int e = 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = a; b < 4; ++b, ++e)
+                    Q[r][zi][e] = w00 * G[2 * a][2 * b] + w01 * (G[2 * a][2 * b + 1] + G[2 * a + 1][2 * b]) + w11 * G[2 * a + 1][2 * b + 1];
+        }
+    }
+    const bool vec_ok = (q.z0 & 1) == 0 && (zs & 1) == 0 && (reinterpret_cast<uintptr_t>(q.out) & 7) == 0;
+    const int Hzs = q.H * zs;
+    const size_t n_out = static_cast<size_t>(q.W) * Hzs;
+
+    uint32_t whi[8], wlo[8];
+    if (U == 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint2 f = s_w[j * 32 + lane];
+            whi[j] = f.x;
+            wlo[j] = f.y;
+        }
+    }
+    // store masks, bit (r * 8 + j), for the two z-adjacent elements of a pair.  Valid kx (ky) form a range.
+    // U == 4: j = 2 kx + kyi with ky = 2 kyi + ky_t;  U == 8: j = ky (kx = sub-block, handled per sub-block)
+    uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        uint32_t mr;
+        if (U == 4) {
+            const uint32_t mx = bit_range(-oxb, q.W - oxb);                       // bit kx
+            const uint32_t mx2 = ((mx & 1) * 3u) | (((mx >> 1) & 1) * 12u) | (((mx >> 2) & 1) * 48u) | (((mx >> 3) & 1) * 192u);
+            const uint32_t my = ((oyb[r] >= 0 && oyb[r] < q.H) ? 0x55u : 0u) | ((oyb[r] + 2 >= 0 && oyb[r] + 2 < q.H) ? 0xaau : 0u);
+            mr = mx2 & my;
+        } else {
+            mr = bit_range(-oyb[r], q.H - oyb[r]);
+        }
+        m0 |= zok[r][0] ? mr << (8 * r) : 0u;
+        m1 |= zok[r][1] ? mr << (8 * r) : 0u;
+    }
+    // warp-uniform: every pair is stored whole (or not at all) as one 8-byte word
+    const bool fast_st = __all_sync(0xffffffffu, vec_ok && m0 == m1);
+
+    // dots of the first prototype (software pipeline: prototype a + 1 is in flight while a runs on the tensor cores)
+    // (prototypes a + 1 .. a + UP_PD are in flight while a runs on the tensor cores: the loads are L2 hits, ~1 us away)
+    const float* da = q.dots;
+    const float* const da_last = q.dots + static_cast<size_t>(q.A - 1) * n_lr;
+    float nv[UP_PD][4];
+    // (volatile: the load must stay behind the consumption of the ring slot it refills, or the compiler loads into a
+    // temporary and copies it into the slot -- a copy that waits for the load)
+    auto ldv = [](const float* p) { float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; };
+    auto fetch = [&](float (&v)[4]) {
+        v[0] = ldv(up_ptr_at(da, off[0][0]));
+        v[1] = ldv(up_ptr_at(da, off[0][1]));
+        v[2] = ldv(up_ptr_at(da, off[1][0]));
+        v[3] = ldv(up_ptr_at(da, off[1][1]));
+        da = da < da_last ? da + n_lr : da;                              // (past the end: re-read the last prototype)
+    };
+#pragma unroll
+    for (int i = 0; i < UP_PD; ++i) fetch(nv[i]);
+
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+        uint32_t ms0 = m0, ms1 = m1;
+        if (U == 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint2 f = s_w[(sub * 8 + j) * 32 + lane];
+                whi[j] = f.x;
+                wlo[j] = f.y;
+            }
+            const bool xok = oxb + sub >= 0 && oxb + sub < q.W;
+            ms0 = xok ? m0 : 0u;
+            ms1 = xok ? m1 : 0u;
+        }
+        // ---- 1 / |interp(f)| of the thread's 32 outputs: contract x, then y --------------------------------
+        // Q index e of (a, b), a <= b in (bx, by) = 00, 01, 10, 11: (0,0)=0 (0,1)=1 (0,2)=2 (0,3)=3 (1,1)=4 (1,2)=5 (1,3)=6 (2,2)=7 (2,3)=8 (3,3)=9
+#pragma unroll
+        for (int kxi = 0; kxi < (U == 4 ? 4 : 1); ++kxi) {
+            const int kx = U == 4 ? kxi : sub;
+            const float tx = (kx + 0.5f) / U;
+            const float x00 = (1.0f - tx) * (1.0f - tx), x01 = (1.0f - tx) * tx, x11 = tx * tx;
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int zi = 0; zi < 2; ++zi) {
+                    const float* qq = Q[r][zi];
+                    // R[by][by'] = sum_{bx, bx'} wx wx' Q[(bx,by)][(bx',by')]
+                    const float r00 = x00 * qq[0] + 2.0f * x01 * qq[2] + x11 * qq[7];
+                    const float r01 = x00 * qq[1] + x01 * (qq[3] + qq[5]) + x11 * qq[8];
+                    const float r11 = x00 * qq[4] + 2.0f * x01 * qq[6] + x11 * qq[9];
+#pragma unroll
+                    for (int kyi = 0; kyi < (U == 4 ? 2 : 8); ++kyi) {
+                        const int j = U == 4 ? 2 * kxi + kyi : kyi;
+                        const int ky = U == 4 ? 2 * kyi + ky_t : kyi;
+                        const float ty = (ky + 0.5f) / U;
+                        const float n2 = (1.0f - ty) * (1.0f - ty) * r00 + 2.0f * ty * (1.0f - ty) * r01 + ty * ty * r11;
+                        inv[r][j][zi] = rsqrt_fast(fmaxf(n2, 1e-24f));       // 1 / max(|v|, 1e-12)
+                    }
+                }
+        }
+
+        // ---- per class: running max over its prototypes of the tensor-core interpolated dots ----------------
+        if (U == 8 && sub > 0) {
+            da = q.dots;
+#pragma unroll
+            for (int i = 0; i < UP_PD; ++i) fetch(nv[i]);
+        }
+        float best[2][8][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) best[r][j][0] = best[r][j][1] = -INFINITY;
+        auto tr = [&](float sim) {
+            const float x = fminf(fmaxf(sim, 0.0f), 1.0f);
+            if (EXPK == 0) return x * x;
+            if (EXPK == 1) return x * x * sqrtf(x);
+            if (EXPK == 2) return x;
+            return x > 0.0f ? __powf(x, q.exponent) : 0.0f;
+        };
+        int c = 0, a_end = s_off[1];
+        float* oc = q.out;
+        // flat loop over all prototypes, unrolled by the prefetch distance so that the ring of in-flight corner dots is
+        // indexed statically (a register copy of a value still in flight would wait for it)
+#pragma unroll 1
+        for (int a0 = 0; a0 < q.A; a0 += UP_PD) {
+#pragma unroll
+            for (int i = 0; i < UP_PD; ++i) {
+                if (a0 + i >= q.A) break;
+                const float v00 = nv[i][0], v01 = nv[i][1], v10 = nv[i][2], v11 = nv[i][3];
+                // K = [corner hi | corner hi] x [W_hi | W_lo], then [corner mid | corner mid] x the same B pair
+                uint32_t ah[4], am[4];
+                ah[0] = ptx::pack_bf16x2(v00, v01);
+                ah[1] = ptx::pack_bf16x2(v10, v11);
+                am[0] = ptx::pack_bf16x2(v00 - bf16_lo_f(ah[0]), v01 - bf16_hi_f(ah[0]));
+                am[1] = ptx::pack_bf16x2(v10 - bf16_lo_f(ah[1]), v11 - bf16_hi_f(ah[1]));
+                // opaque copies: the fragment is a register quad, the compiler must see four distinct values to keep it alive
+                asm volatile("mov.b32 %0, %1;" : "=r"(ah[2]) : "r"(ah[0]));
+                asm volatile("mov.b32 %0, %1;" : "=r"(ah[3]) : "r"(ah[1]));
+                asm volatile("mov.b32 %0, %1;" : "=r"(am[2]) : "r"(am[0]));
+                asm volatile("mov.b32 %0, %1;" : "=r"(am[3]) : "r"(am[1]));
+                fetch(nv[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float dd[4];
+                    mma_bf16_16816_z(dd, ah, whi[j], wlo[j]);
+                    mma_bf16_16816(dd, am, whi[j], wlo[j]);
+                    best[0][j][0] = fmaxf(best[0][j][0], dd[0]);
+                    best[0][j][1] = fmaxf(best[0][j][1], dd[1]);
+                    best[1][j][0] = fmaxf(best[1][j][0], dd[2]);
+                    best[1][j][1] = fmaxf(best[1][j][1], dd[3]);
+                }
+                if (a0 + i + 1 != a_end) continue;
+                // ---- last prototype of class c: normalise, clamp(0,1)^e, store ------------------------------
+                if (fast_st) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int joff = U == 4 ? (j >> 1) * Hzs + 2 * (j & 1) * zs : sub * Hzs + j * zs;
+                            const float r0 = tr(best[r][j][0] * inv[r][j][0]), r1 = tr(best[r][j][1] * inv[r][j][1]);
+                            if ((ms0 >> (r * 8 + j)) & 1) *reinterpret_cast<float2*>(up_out_at(oc, obase[r] + joff)) = make_float2(r0, r1);
+                        }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int joff = U == 4 ? (j >> 1) * Hzs + 2 * (j & 1) * zs : sub * Hzs + j * zs;
+                            const float r0 = tr(best[r][j][0] * inv[r][j][0]), r1 = tr(best[r][j][1] * inv[r][j][1]);
+                            float* dst = up_out_at(oc, obase[r] + joff);
+                            if ((ms0 >> (r * 8 + j)) & 1) dst[0] = r0;
+                            if ((ms1 >> (r * 8 + j)) & 1) dst[1] = r1;
+                        }
+                }
+                ++c;
+                oc += n_out;
+                a_end = c < q.C ? s_off[c + 1] : -1;
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) best[r][j][0] = best[r][j][1] = -INFINITY;
+            }
+        }
+    }
+}
+
+template <int U>
+int launch_upsample_mma(const UpParams& q, cudaStream_t s) {
+    auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+    const int cz_lo = fdiv(q.z0 - U / 2, U), cz_hi = fdiv(q.z1 - 1 - U / 2, U);
+    const int ncz = cz_hi - cz_lo + 1;
+    const int tiles_per_x = ceil_div((q.h + 1) * ncz, 16);
+    const long long total = static_cast<long long>(q.w + 1) * tiles_per_x;
+    if (total > 0x7fffffff / 4) return -1;
+    const size_t smem = (((q.C + 1) * 4 + 15) & ~15) + (U == 8 ? 64 : 8) * 32 * sizeof(uint2);
+    const unsigned grid = static_cast<unsigned>((total + 3) / 4);
+    const int tt = static_cast<int>(total);
+    if (q.exponent == 2.0f) sim_upsample_mma_kernel<U, 0><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt);
+    else if (q.exponent == 2.5f) sim_upsample_mma_kernel<U, 1><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt);
+    else if (q.exponent == 1.0f) sim_upsample_mma_kernel<U, 2><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt);
+    else sim_upsample_mma_kernel<U, 3><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // pass 2, row kernel for integer up-sampling factors U in {2, 4, 8} of a cubic grid (the benchmark shapes).
 // One CTA owns one output x index and `cyb` low-res cell rows in y; per chunk of <= `ac` prototypes it
 //   1. interpolates the corner dots in x and y ONCE per (cell row, prototype, low-res z) into shared memory
@@ -1363,6 +1715,21 @@ extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, i
     // integer power-of-two up-sampling of a cubic grid, max-type modes: separable cell kernel
     const bool cubic = w == h && h == d && W == H && H == D && W % w == 0;
     const int U = cubic ? W / w : 0;
+    // any grid whose three factors are the same U in {4, 8}: tensor-core cell-tile kernel
+    if (mode == VITTF_SIM_NS && (W == 4 * w || W == 8 * w) && H * static_cast<int64_t>(w) == static_cast<int64_t>(h) * W &&
+        D * static_cast<int64_t>(w) == static_cast<int64_t>(d) * W && static_cast<int64_t>(W) * H * (z1 - z0) < (1ll << 30) &&
+        static_cast<int64_t>(w) * h * d < (1ll << 31)) {
+        static const bool no_mma = getenv("VITTF_SIM_UP_NO_MMA") != nullptr;   // A/B switch: FMA-pipe cell kernel
+        if (!no_mma) {
+            cudaStream_t s = static_cast<cudaStream_t>(stream);
+            const int rc = W == 4 * w ? launch_upsample_mma<4>(q, s) : launch_upsample_mma<8>(q, s);
+            if (rc == 0) {
+                VITTF_CHECK_CUDA(cudaGetLastError());
+                vittf_count_launches(1);
+                return VITTF_OK;
+            }
+        }
+    }
     if (cubic && mode != VITTF_SIM_REFNTF && (U == 2 || U == 4 || U == 8) && mode == VITTF_SIM_NS) {
         static const bool use_rows = getenv("VITTF_SIM_ROWS") != nullptr;    // A/B switch: shared-memory row kernel
         cudaStream_t s = static_cast<cudaStream_t>(stream);
