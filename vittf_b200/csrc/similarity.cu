@@ -595,13 +595,13 @@ int launch_dots_mma_one(const CUtensorMap& tm, int F, int64_t n, const float* pr
 }
 
 // all prototypes, 64 per launch
-int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, int A, float* dots, cudaStream_t s) {
+int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, int A, float* dots, cudaStream_t s, int a_first = 0) {
     CUtensorMap tm;
     const uint64_t dims[2] = {static_cast<uint64_t>(n), static_cast<uint64_t>(F)};
     const uint64_t strides[1] = {static_cast<uint64_t>(n) * 2};
     const uint32_t box[2] = {64, DM_BK};
     VITTF_CHECK(vittf_make_tmap(&tm, feats, 2, 2, dims, strides, box, true));
-    for (int a_base = 0; a_base < A; a_base += 64) {
+    for (int a_base = a_first; a_base < A; a_base += 64) {
         const int rem = A - a_base;
         int rc;
         if (rem > 32) rc = launch_dots_mma_one<8>(tm, F, n, protos, A, a_base, dots, s);
@@ -610,6 +610,233 @@ int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, 
         else rc = launch_dots_mma_one<1>(tm, F, n, protos, A, a_base, dots, s);
         VITTF_CHECK(rc);
     }
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    return VITTF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1 fused on the tensor cores: prototype dots AND the 14 Gram planes from ONE read of the fp16 feature volume.
+// The Gram entry of voxel v and forward neighbour v + (dx, dy, dz) is a dot product over F, so for a tile of 16 z-adjacent
+// voxels (an m16 tile) the products with the 8-voxel tiles of the five neighbour z-lines (dx, dy) in {(0,0), (0,1), (1,-1),
+// (1,0), (1,1)} are m16n8k16 MMAs whose +-1 diagonals are the wanted entries: 3 + 4 x 4 n-tiles per k16 step, plus A / 8
+// n-tiles for the prototypes -- 23 HMMA instead of 14 x 16 x 16 + 32 x 16 x 16 FMAs.  ldmatrix.trans turns the staged
+// [f][line][z] rows into A fragments, and the SAME registers are the B fragments of the two 8-voxel halves (a 16 x 16 block
+// loaded once serves both roles).  Persistent CTAs: 8 consumer warps (2 lines x 64 z = 8 m-tiles per tile) + 1 TMA producer
+// warp that keeps a ring of 16-feature stages full across tile boundaries (3 boxes per stage: lines y0..y0+2 of plane x,
+// y0-1..y0+1 and y0+2 of plane x+1; out-of-volume coordinates are zero-filled = the "no neighbour" convention).  The box is
+// 88 voxels long in z ([tz0 - 8, tz0 + 80)) so that the per-feature strides (528 / 176 B) are odd multiples of 16 B:
+// every ldmatrix phase is bank-conflict free.
+// ---------------------------------------------------------------------------------------------
+constexpr int GM_ZB = 88, GM_TZ = 64, GM_KF = 16;
+constexpr int GM_L1 = GM_ZB * 2;                          // bytes of one staged z-line of one feature
+constexpr int GM_L3 = 3 * GM_L1;                          // per-feature stride of a 3-line box
+constexpr int GM_OFF_P = GM_KF * GM_L3, GM_OFF_Q = 2 * GM_KF * GM_L3;
+constexpr int GM_STAGE = GM_KF * (2 * GM_L3 + GM_L1);     // 19712
+constexpr int GM_CONSUMERS = 8;
+
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+template <int NT>   // n-tiles of 8 prototypes (A <= 8 * NT)
+__global__ void __maxnreg__(168)
+    sim_lowres_mma_kernel(const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm1, int F, int w, int h, int d,
+                          const float* __restrict__ protos, int A, float* __restrict__ dots, float* __restrict__ gram,
+                          int tiles_y, int tiles_z, int ntiles, int nstages) {
+    extern __shared__ __align__(1024) uint8_t gm_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gm_raw) + 127) & ~uintptr_t(127));
+    uint8_t* s_t = smem;                                                                   // [stage][X | P | Q]
+    __half* s_p = reinterpret_cast<__half*>(smem + static_cast<size_t>(nstages) * GM_STAGE);   // [8 NT][F + 8]
+    const int pstride = F + 8;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_p + static_cast<size_t>(8 * NT) * pstride);
+    uint64_t* empty = full + nstages;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nchunk = F / GM_KF;
+    if (tid == 0) {
+        for (int i = 0; i < nstages; ++i) {
+            ptx::mbar_init(&full[i], 1);
+            ptx::mbar_init(&empty[i], GM_CONSUMERS);
+        }
+        ptx::fence_barrier_init();
+    }
+    for (int i = tid; i < 8 * NT * pstride; i += blockDim.x) {
+        const int a = i / pstride, ff = i - a * pstride;
+        s_p[i] = __float2half_rn(a < A && ff < F ? protos[static_cast<size_t>(a) * F + ff] : 0.0f);
+    }
+    __syncthreads();
+
+    if (wid == GM_CONSUMERS) {
+        // ---- TMA producer ------------------------------------------------------------------------------------
+        if (lane == 0) {
+            ptx::prefetch_tmap(&tm3);
+            ptx::prefetch_tmap(&tm1);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int zb = tile % tiles_z, yb = (tile / tiles_z) % tiles_y, x = tile / (tiles_z * tiles_y);
+                const int tz = zb * GM_TZ - 8, y0 = yb * 2;
+                for (int c = 0; c < nchunk; ++c, ++it) {
+                    const int st = it % nstages;
+                    if (it >= nstages) ptx::mbar_wait(&empty[st], ((it / nstages) & 1) ^ 1);
+                    uint8_t* dst = s_t + static_cast<size_t>(st) * GM_STAGE;
+                    ptx::mbar_arrive_expect_tx(&full[st], GM_STAGE);
+                    ptx::tma_load_4d(dst, &tm3, &full[st], tz, y0, x, c * GM_KF);
+                    ptx::tma_load_4d(dst + GM_OFF_P, &tm3, &full[st], tz, y0 - 1, x + 1, c * GM_KF);
+                    ptx::tma_load_4d(dst + GM_OFF_Q, &tm1, &full[st], tz, y0 + 2, x + 1, c * GM_KF);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: warp = (line li, z tile zt) ----------------------------------------------------------------
+    const int li = wid >> 2, zt = wid & 3;
+    const int g = lane >> 2, t = lane & 3;
+    const int mi = lane >> 3, mr = lane & 7;
+    // per-lane ldmatrix row offsets for the two per-feature strides
+    // A order (own line): matrices (v 0-7, f 0-7) (v 8-15, f 0-7) (v 0-7, f 8-15) (v 8-15, f 8-15);
+    // B order (neighbour windows): (v 0-7, f 0-7) (v 0-7, f 8-15) (v 8-15, f 0-7) (v 8-15, f 8-15) -> register pairs = B fragments
+    const uint32_t lo3a = (8 * (mi >> 1) + mr) * GM_L3 + 16 * (mi & 1);
+    const uint32_t lo3 = (8 * (mi & 1) + mr) * GM_L3 + 16 * (mi >> 1), lo1 = (8 * (mi & 1) + mr) * GM_L1 + 16 * (mi >> 1);
+    const uint32_t lo3x2 = (8 * (mi & 1) + mr) * GM_L3;                      // x2: matrices (f 0-7), (f 8-15) of 8 voxels
+    const uint32_t zc0 = (8 + 16 * zt) * 2;                                  // byte offset of the m-tile's first voxel in a staged line
+    // neighbour lines (dx, dy): (0,1), (1,-1), (1,0), (1,1)
+    uint32_t nb_off[4];
+    nb_off[0] = (li + 1) * GM_L1 + lo3;
+    nb_off[1] = GM_OFF_P + li * GM_L1 + lo3;
+    nb_off[2] = GM_OFF_P + (li + 1) * GM_L1 + lo3;
+    nb_off[3] = li == 0 ? GM_OFF_P + 2 * GM_L1 + lo3 : GM_OFF_Q + lo1;
+    const uint32_t own_off = li * GM_L1 + lo3a + zc0, own_x2 = li * GM_L1 + lo3x2 + zc0 + 32;
+    const uint32_t st_base = ptx::smem_u32(s_t);
+    const uint32_t p_base = ptx::smem_u32(s_p);
+    const int64_t n = static_cast<int64_t>(w) * h * d;
+
+    float acc_o[3][4], acc_n[4][4][4], acc_d[NT][4];
+    auto zero_acc = [&]() {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) acc_o[i][e] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc_n[k][i][e] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc_d[j][e] = 0.0f;
+        }
+    };
+    zero_acc();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunk; ++c, ++it) {
+            const int st = it % nstages;
+            ptx::mbar_wait(&full[st], (it / nstages) & 1);
+            const uint32_t sb = st_base + st * GM_STAGE;
+            uint32_t a[4];
+            ldmatrix_x4_trans(sb + own_off, a);
+            {
+                uint32_t b0, b1;
+                ldmatrix_x2_trans(sb + own_x2, b0, b1);
+                mma_f16_16816(acc_o[0], a, a[0], a[2]);
+                mma_f16_16816(acc_o[1], a, a[1], a[3]);
+                mma_f16_16816(acc_o[2], a, b0, b1);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t w0[4], w1[4];
+                ldmatrix_x4_trans(sb + nb_off[k] + zc0 - 16, w0);            // voxels [z0 - 8, z0 + 8)
+                ldmatrix_x4_trans(sb + nb_off[k] + zc0 + 16, w1);            // voxels [z0 + 8, z0 + 24)
+                mma_f16_16816(acc_n[k][0], a, w0[0], w0[1]);
+                mma_f16_16816(acc_n[k][1], a, w0[2], w0[3]);
+                mma_f16_16816(acc_n[k][2], a, w1[0], w1[1]);
+                mma_f16_16816(acc_n[k][3], a, w1[2], w1[3]);
+            }
+#pragma unroll
+            for (int j = 0; j < NT; j += 2) {
+                // B fragments of prototypes [8j, 8j+16): matrices (n0:8,k0:8) (n0:8,k8:16) (n8:16,k0:8) (n8:16,k8:16)
+                uint32_t bf[4];
+                const int prow = 8 * j + ((NT > 1) ? (mi >> 1) * 8 : 0) + mr;
+                ldmatrix_x4(p_base + (prow * pstride + c * GM_KF + (mi & 1) * 8) * 2, bf);
+                mma_f16_16816(acc_d[j], a, bf[0], bf[1]);
+                if (j + 1 < NT) mma_f16_16816(acc_d[j + 1], a, bf[2], bf[3]);
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[st]);
+        }
+        // ---- tile epilogue: the wanted diagonals of the accumulators -> gram planes, prototype columns -> dots --------
+        const int zb = tile % tiles_z, yb = (tile / tiles_z) % tiles_y, x = tile / (tiles_z * tiles_y);
+        const int y = yb * 2 + li, z0 = zb * GM_TZ + 16 * zt;
+        const bool yok = y < h;
+        const int64_t vb = (static_cast<int64_t>(x) * h + y) * d + z0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int row = g + 8 * (e >> 1);
+            const bool ok = yok && z0 + row < d;
+            const int cb = 2 * t + (e & 1) - row;                           // column - row, before the tile offset
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int aa = 8 * j + 2 * t + (e & 1);
+                if (ok && aa < A) dots[static_cast<int64_t>(aa) * n + vb + row] = acc_d[j][e];
+            }
+            if (gram != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int dz = 8 * i + cb;
+                    if (ok && dz == 0) gram[vb + row] = acc_o[i][e];
+                    if (ok && dz == 1) gram[13 * n + vb + row] = acc_o[i][e];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int slot0 = k == 0 ? 11 : 3 * k - 1;              // slot of dz = 0: (0,1) -> 11, (1,-1) -> 2, (1,0) -> 5, (1,1) -> 8
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int dz = 8 * i - 8 + cb;
+                        if (ok && dz >= -1 && dz <= 1) gram[static_cast<int64_t>(slot0 + dz) * n + vb + row] = acc_n[k][i][e];
+                    }
+                }
+            }
+        }
+        zero_acc();
+    }
+}
+
+template <int NT>
+int launch_lowres_mma_one(const CUtensorMap& tm3, const CUtensorMap& tm1, int F, int w, int h, int d, const float* protos, int A,
+                          float* dots, float* gram, cudaStream_t s) {
+    const int tiles_z = ceil_div(d, GM_TZ), tiles_y = ceil_div(h, 2);
+    const int ntiles = tiles_z * tiles_y * w;
+    const size_t panel = static_cast<size_t>(8 * NT) * (F + 8) * 2;
+    int nstages = static_cast<int>((220 * 1024 - panel - 256) / GM_STAGE);
+    nstages = nstages > 8 ? 8 : nstages;
+    if (nstages < 3) return -1;
+    const size_t smem = static_cast<size_t>(nstages) * GM_STAGE + panel + 2 * nstages * 8 + 128;
+    auto kern = sim_lowres_mma_kernel<NT>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = smem;
+    }
+    const int grid = ntiles < vittf_num_sms() ? ntiles : vittf_num_sms();
+    kern<<<grid, 32 * (GM_CONSUMERS + 1), smem, s>>>(tm3, tm1, F, w, h, d, protos, A, dots, gram, tiles_y, tiles_z, ntiles, nstages);
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
+
+// first <= 32 prototypes + Gram planes fused; prototypes beyond 32 on the dots-only tensor-core kernel
+int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const float* protos, int A, float* dots, float* gram,
+                      cudaStream_t s) {
+    CUtensorMap tm3, tm1;
+    const uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint64_t>(w), static_cast<uint64_t>(F)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(h) * d * 2, static_cast<uint64_t>(w) * h * d * 2};
+    const uint32_t box3[4] = {GM_ZB, 3, 1, GM_KF}, box1[4] = {GM_ZB, 1, 1, GM_KF};
+    VITTF_CHECK(vittf_make_tmap(&tm3, feats, 2, 4, dims, strides, box3, false));
+    VITTF_CHECK(vittf_make_tmap(&tm1, feats, 2, 4, dims, strides, box1, false));
+    const int a0 = A < 32 ? A : 32;
+    int rc;
+    if (a0 > 16) rc = launch_lowres_mma_one<4>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, s);
+    else if (a0 > 8) rc = launch_lowres_mma_one<2>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, s);
+    else rc = launch_lowres_mma_one<1>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, s);
+    if (rc != VITTF_OK) return rc;
+    if (A > 32) VITTF_CHECK(launch_dots_mma(feats, F, static_cast<int64_t>(w) * h * d, protos, A, dots, s, 32));
     VITTF_CHECK_CUDA(cudaGetLastError());
     return VITTF_OK;
 }
@@ -628,6 +855,11 @@ int launch_lowres_tma(const __half* feats, int F, int w, int h, int d, const flo
     int a_base = 0;
     const int64_t n = static_cast<int64_t>(w) * h * d;
     static const bool no_mma = getenv("VITTF_SIM_NO_MMA") != nullptr;     // A/B switch: FFMA2 dots
+    static const bool no_fused = getenv("VITTF_SIM_NO_FUSED") != nullptr; // A/B switch: dots (tensor cores) + Gram (FMA pipe) as two kernels
+    if (!no_mma && !no_fused && F % DM_BK == 0 && d % 8 == 0) {
+        const int rc = launch_lowres_mma(feats, F, w, h, d, protos, A, dots, GRAM ? gram : nullptr, s);
+        if (rc != -1) return rc;
+    }
     if (!no_mma && F % DM_BK == 0 && n % 8 == 0) {
         // dots of all prototypes on the tensor cores; the Gram planes (the only part that needs the halo) on the FMA pipe
         VITTF_CHECK(launch_dots_mma(feats, F, n, protos, A, dots, s));
@@ -1053,6 +1285,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
     int* s_off = reinterpret_cast<int*>(um_smem);
     uint2* s_w = reinterpret_cast<uint2*>(um_smem + (((q.C + 1) * 4 + 15) & ~15));   // [sub][ntile][lane]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+
     for (int i = threadIdx.x; i <= q.C; i += 128) s_off[i] = q.class_offsets[i];
 #pragma unroll 1
     for (int i = threadIdx.x; i < NSUB * 8 * 32; i += 128) {
