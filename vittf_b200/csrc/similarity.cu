@@ -659,9 +659,18 @@ __global__ void __maxnreg__(168)
         }
         ptx::fence_barrier_init();
     }
-    for (int i = tid; i < 8 * NT * pstride; i += blockDim.x) {
-        const int a = i / pstride, ff = i - a * pstride;
-        s_p[i] = __float2half_rn(a < A && ff < F ? protos[static_cast<size_t>(a) * F + ff] : 0.0f);
+    // prototype panel (fp16, rows padded by 8 halves): one prototype per warp pass, 4 independent loads per lane in flight
+    for (int a = wid; a < 8 * NT; a += GM_CONSUMERS + 1) {
+        __half* row = s_p + static_cast<size_t>(a) * pstride;
+        const float* src = protos + static_cast<size_t>(a) * F;
+        for (int f0 = lane; f0 < pstride; f0 += 128) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (a < A && f0 + 32 * u < F) ? __ldg(src + f0 + 32 * u) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (f0 + 32 * u < pstride) row[f0 + 32 * u] = __float2half_rn(v[u]);
+        }
     }
     __syncthreads();
 
@@ -670,18 +679,24 @@ __global__ void __maxnreg__(168)
         if (lane == 0) {
             ptx::prefetch_tmap(&tm3);
             ptx::prefetch_tmap(&tm1);
-            int it = 0;
+            int st = 0;
+            uint32_t ph = 0;                                  // parity of the phase that releases the stage's previous use
+            bool first_round = true;                          // (nothing to wait for while the ring fills for the first time)
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int zb = tile % tiles_z, yb = (tile / tiles_z) % tiles_y, x = tile / (tiles_z * tiles_y);
                 const int tz = zb * GM_TZ - 8, y0 = yb * 2;
-                for (int c = 0; c < nchunk; ++c, ++it) {
-                    const int st = it % nstages;
-                    if (it >= nstages) ptx::mbar_wait(&empty[st], ((it / nstages) & 1) ^ 1);
+                for (int c = 0; c < nchunk; ++c) {
+                    if (!first_round) ptx::mbar_wait_quiet(&empty[st], ph);
                     uint8_t* dst = s_t + static_cast<size_t>(st) * GM_STAGE;
                     ptx::mbar_arrive_expect_tx(&full[st], GM_STAGE);
                     ptx::tma_load_4d(dst, &tm3, &full[st], tz, y0, x, c * GM_KF);
                     ptx::tma_load_4d(dst + GM_OFF_P, &tm3, &full[st], tz, y0 - 1, x + 1, c * GM_KF);
                     ptx::tma_load_4d(dst + GM_OFF_Q, &tm1, &full[st], tz, y0 + 2, x + 1, c * GM_KF);
+                    if (++st == nstages) {
+                        st = 0;
+                        if (!first_round) ph ^= 1u;
+                        first_round = false;
+                    }
                 }
             }
         }
@@ -725,42 +740,50 @@ __global__ void __maxnreg__(168)
         }
     };
     zero_acc();
-    int it = 0;
+    int st = 0;
+    uint32_t ph = 0;
+    uint32_t sb = st_base;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int c = 0; c < nchunk; ++c, ++it) {
-            const int st = it % nstages;
-            ptx::mbar_wait(&full[st], (it / nstages) & 1);
-            const uint32_t sb = st_base + st * GM_STAGE;
-            uint32_t a[4];
+        uint32_t pk = p_base + (((NT > 1 ? (mi >> 1) * 8 : 0) + mr) * pstride + (mi & 1) * 8) * 2;   // panel ldmatrix row of this lane
+#pragma unroll 1
+        for (int c = 0; c < nchunk; ++c) {
+            ptx::mbar_wait_quiet(&full[st], ph);
+            // all fragments of the k-step first (11 + NT/2 ldmatrix in flight), then the MMAs
+            uint32_t a[4], o2[2], w0[4][4], w1[4][4], bf[(NT + 1) / 2][4];
             ldmatrix_x4_trans(sb + own_off, a);
-            {
-                uint32_t b0, b1;
-                ldmatrix_x2_trans(sb + own_x2, b0, b1);
-                mma_f16_16816(acc_o[0], a, a[0], a[2]);
-                mma_f16_16816(acc_o[1], a, a[1], a[3]);
-                mma_f16_16816(acc_o[2], a, b0, b1);
-            }
+            ldmatrix_x2_trans(sb + own_x2, o2[0], o2[1]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                uint32_t w0[4], w1[4];
-                ldmatrix_x4_trans(sb + nb_off[k] + zc0 - 16, w0);            // voxels [z0 - 8, z0 + 8)
-                ldmatrix_x4_trans(sb + nb_off[k] + zc0 + 16, w1);            // voxels [z0 + 8, z0 + 24)
-                mma_f16_16816(acc_n[k][0], a, w0[0], w0[1]);
-                mma_f16_16816(acc_n[k][1], a, w0[2], w0[3]);
-                mma_f16_16816(acc_n[k][2], a, w1[0], w1[1]);
-                mma_f16_16816(acc_n[k][3], a, w1[2], w1[3]);
+                ldmatrix_x4_trans(sb + nb_off[k] + zc0 - 16, w0[k]);         // voxels [z0 - 8, z0 + 8)
+                ldmatrix_x4_trans(sb + nb_off[k] + zc0 + 16, w1[k]);         // voxels [z0 + 8, z0 + 24)
+            }
+            // B fragments of prototypes [8j, 8j+16): matrices (n0:8,k0:8) (n0:8,k8:16) (n8:16,k0:8) (n8:16,k8:16)
+#pragma unroll
+            for (int j = 0; j < NT; j += 2) ldmatrix_x4(pk + 16 * j * pstride, bf[j / 2]);
+            pk += GM_KF * 2;
+            mma_f16_16816(acc_o[0], a, a[0], a[2]);
+            mma_f16_16816(acc_o[1], a, a[1], a[3]);
+            mma_f16_16816(acc_o[2], a, o2[0], o2[1]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                mma_f16_16816(acc_n[k][0], a, w0[k][0], w0[k][1]);
+                mma_f16_16816(acc_n[k][1], a, w0[k][2], w0[k][3]);
+                mma_f16_16816(acc_n[k][2], a, w1[k][0], w1[k][1]);
+                mma_f16_16816(acc_n[k][3], a, w1[k][2], w1[k][3]);
             }
 #pragma unroll
             for (int j = 0; j < NT; j += 2) {
-                // B fragments of prototypes [8j, 8j+16): matrices (n0:8,k0:8) (n0:8,k8:16) (n8:16,k0:8) (n8:16,k8:16)
-                uint32_t bf[4];
-                const int prow = 8 * j + ((NT > 1) ? (mi >> 1) * 8 : 0) + mr;
-                ldmatrix_x4(p_base + (prow * pstride + c * GM_KF + (mi & 1) * 8) * 2, bf);
-                mma_f16_16816(acc_d[j], a, bf[0], bf[1]);
-                if (j + 1 < NT) mma_f16_16816(acc_d[j + 1], a, bf[2], bf[3]);
+                mma_f16_16816(acc_d[j], a, bf[j / 2][0], bf[j / 2][1]);
+                if (j + 1 < NT) mma_f16_16816(acc_d[j + 1], a, bf[j / 2][2], bf[j / 2][3]);
             }
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&empty[st]);
+            sb += GM_STAGE;
+            if (++st == nstages) {
+                st = 0;
+                ph ^= 1;
+                sb = st_base;
+            }
         }
         // ---- tile epilogue: the wanted diagonals of the accumulators -> gram planes, prototype columns -> dots --------
         const int zb = tile % tiles_z, yb = (tile / tiles_z) % tiles_y, x = tile / (tiles_z * tiles_y);
