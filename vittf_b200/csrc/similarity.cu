@@ -1500,11 +1500,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
 #pragma unroll
             for (int i = 0; i < UP_PD; ++i) fetch(nv[i]);
         }
-        float best[2][8][2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) best[r][j][0] = best[r][j][1] = -INFINITY;
+        float best[8][4];            // accumulator-fragment layout: [n-tile][(row g, col 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1)]
         auto tr = [&](float sim) {
             const float x = fminf(fmaxf(sim, 0.0f), 1.0f);
             if (EXPK == 0) return x * x;
@@ -1512,7 +1508,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
             if (EXPK == 2) return x;
             return x > 0.0f ? __powf(x, q.exponent) : 0.0f;
         };
-        int c = 0, a_end = s_off[1];
+        int c = 0, a_begin = 0, a_end = s_off[1];
         float* oc = q.out;
         // flat loop over all prototypes, unrolled by the prefetch distance so that the ring of in-flight corner dots is
         // indexed statically (a register copy of a value still in flight would wait for it)
@@ -1534,15 +1530,22 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
                 asm volatile("mov.b32 %0, %1;" : "=r"(am[2]) : "r"(am[0]));
                 asm volatile("mov.b32 %0, %1;" : "=r"(am[3]) : "r"(am[1]));
                 fetch(nv[i]);
+                if (a0 + i == a_begin) {
+                    // first prototype of the class: the MMAs write the running maximum directly (no reset, no max)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float dd[4];
-                    mma_bf16_16816_z(dd, ah, whi[j], wlo[j]);
-                    mma_bf16_16816(dd, am, whi[j], wlo[j]);
-                    best[0][j][0] = fmaxf(best[0][j][0], dd[0]);
-                    best[0][j][1] = fmaxf(best[0][j][1], dd[1]);
-                    best[1][j][0] = fmaxf(best[1][j][0], dd[2]);
-                    best[1][j][1] = fmaxf(best[1][j][1], dd[3]);
+                    for (int j = 0; j < 8; ++j) {
+                        mma_bf16_16816_z(best[j], ah, whi[j], wlo[j]);
+                        mma_bf16_16816(best[j], am, whi[j], wlo[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float dd[4];
+                        mma_bf16_16816_z(dd, ah, whi[j], wlo[j]);
+                        mma_bf16_16816(dd, am, whi[j], wlo[j]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) best[j][e] = fmaxf(best[j][e], dd[e]);
+                    }
                 }
                 if (a0 + i + 1 != a_end) continue;
                 // ---- last prototype of class c: normalise, clamp(0,1)^e, store ------------------------------
@@ -1552,7 +1555,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int joff = U == 4 ? (j >> 1) * Hzs + 2 * (j & 1) * zs : sub * Hzs + j * zs;
-                            const float r0 = tr(best[r][j][0] * inv[r][j][0]), r1 = tr(best[r][j][1] * inv[r][j][1]);
+                            const float r0 = tr(best[j][2 * r] * inv[r][j][0]), r1 = tr(best[j][2 * r + 1] * inv[r][j][1]);
                             if ((ms0 >> (r * 8 + j)) & 1) *reinterpret_cast<float2*>(up_out_at(oc, obase[r] + joff)) = make_float2(r0, r1);
                         }
                 } else {
@@ -1561,7 +1564,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int joff = U == 4 ? (j >> 1) * Hzs + 2 * (j & 1) * zs : sub * Hzs + j * zs;
-                            const float r0 = tr(best[r][j][0] * inv[r][j][0]), r1 = tr(best[r][j][1] * inv[r][j][1]);
+                            const float r0 = tr(best[j][2 * r] * inv[r][j][0]), r1 = tr(best[j][2 * r + 1] * inv[r][j][1]);
                             float* dst = up_out_at(oc, obase[r] + joff);
                             if ((ms0 >> (r * 8 + j)) & 1) dst[0] = r0;
                             if ((ms1 >> (r * 8 + j)) & 1) dst[1] = r1;
@@ -1569,11 +1572,8 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
                 }
                 ++c;
                 oc += n_out;
+                a_begin = a_end;
                 a_end = c < q.C ? s_off[c + 1] : -1;
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) best[r][j][0] = best[r][j][1] = -INFINITY;
             }
         }
     }
