@@ -145,6 +145,33 @@ def ns_composite_direct(feats, protos, class_offsets, out_shape, exponent=2.0):
                         for c in range(len(class_offsets) - 1)])
 
 
+def ns_at_voxels(feats, protos, class_offsets, out_shape, voxels, exponent=2.0):
+    """NS similarity of selected OUTPUT voxels only (full-size spot checks: the slab oracle needs minutes at 512^3).
+    Restates the index rule of F.interpolate(mode='trilinear', align_corners=False) -- src = max((dst + 0.5) * in / out
+    - 0.5, 0), i0 = floor(src), i1 = min(i0 + 1, in - 1), t = src - i0 -- on the 8 corners of each voxel; pinned to
+    ns_composite by tests/test_oracle.py::test_ns_point_oracle_equals_slab_oracle.  voxels (M,3) long -> (C, M) fp32."""
+    pn = F.normalize(protos.float(), dim=-1)
+    dims = feats.shape[1:]
+    idx, wgt = [], []
+    for ax in range(3):
+        src = ((voxels[:, ax].double() + 0.5) * (dims[ax] / out_shape[ax]) - 0.5).clamp_min(0.0)
+        i0 = src.floor().long()
+        i1 = (i0 + 1).clamp_max(dims[ax] - 1)
+        t = (src - i0).float()
+        idx.append((i0, i1))
+        wgt.append((1.0 - t, t))
+    up = torch.zeros(voxels.size(0), feats.size(0), dtype=torch.float32)
+    for bx in range(2):
+        for by in range(2):
+            for bz in range(2):
+                w = wgt[0][bx] * wgt[1][by] * wgt[2][bz]
+                up += w[:, None] * feats[:, idx[0][bx], idx[1][by], idx[2][bz]].float().t()
+    up = F.normalize(up, dim=1)
+    s = (up @ pn.t()).clamp(0, 1) ** exponent                                     # (M, A)
+    return torch.stack([s[:, class_offsets[c]:class_offsets[c + 1]].max(dim=1).values
+                        for c in range(len(class_offsets) - 1)])
+
+
 def compose_labels(sims_u8, thresholds):
     """predict_ntf.py:203-215: thresholded running arg-max, strict '>', 0 = background.
     sims_u8 (C,...) uint8; thresholds list of floats in [0,1]."""

@@ -115,6 +115,45 @@ def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
     assert torch.equal(lab[margin > 1e-2], ref_lab[margin > 1e-2])
 
 
+@pytest.mark.parametrize("F_,n,N,A,C", [(384, 64, 256, 32, 8), (768, 64, 512, 64, 16), (384, 128, 512, 24, 8)])
+def test_ns_similarity_full_size(F_, n, N, A, C):
+    """BASELINE.json shapes (configs[1], [2], [3]): spot check of 4096 random + all-corner output voxels against the point
+    oracle (2e-3), and the size-independent properties of the stage -- z-slab sharding invariance (bit-exact), invariance
+    to the order of a class's prototypes (bit-exact), invariance to a power-of-two scale of the features (the NS
+    composition normalises; bit-exact because every product scales exactly), values in [0, 1]."""
+    from oracle import similarity as osim, synth
+    from vittf_b200.similarity import similarity_maps
+    feats, protos = synth.class_features(F_, (n, n, n), C, seed=4, dtype=torch.float16)
+    g = torch.Generator().manual_seed(21)
+    offs = [round(i * A / C) for i in range(C + 1)]
+    owner = torch.tensor([c for c in range(C) for _ in range(offs[c + 1] - offs[c])])
+    p = F.normalize(protos[owner] + 0.05 * torch.randn(A, F_, generator=g), dim=-1)
+    fc, pc = feats.cuda(), p.cuda().contiguous()
+    oc = torch.tensor(offs, dtype=torch.int32, device="cuda")
+    out = similarity_maps(fc, pc, oc, (N, N, N), mode="ns", exponent=2.0)
+    assert out.shape == (C, N, N, N)
+    assert out.min().item() >= 0.0 and out.max().item() <= 1.0 and torch.isfinite(out).all()
+    vox = torch.randint(0, N, (4096, 3), generator=g)
+    edge = torch.tensor([[x, y, z] for x in (0, 1, N - 2, N - 1) for y in (0, 2, N - 1) for z in (0, 1, 3, N - 1)])
+    vox = torch.cat([vox, edge])
+    ref = osim.ns_at_voxels(feats, p, offs, (N, N, N), vox)
+    got = out[:, vox[:, 0].cuda(), vox[:, 1].cuda(), vox[:, 2].cuda()].cpu()
+    assert (got - ref).abs().max().item() < TOL
+    # z-slab sharding (the multi-GPU unit): 3 uneven slabs reproduce the full volume bit-exactly
+    cuts = [0, N // 4 + 2, N // 2 + 8, N]
+    for z0, z1 in zip(cuts[:-1], cuts[1:]):
+        zs = similarity_maps(fc, pc, oc, (N, N, N), mode="ns", exponent=2.0, z_range=(z0, z1))
+        assert torch.equal(zs, out[..., z0:z1])
+    del zs
+    # prototype order inside a class
+    perm = torch.cat([torch.arange(offs[c], offs[c + 1]).flip(0) for c in range(C)])
+    out2 = similarity_maps(fc, pc[perm.cuda()].contiguous(), oc, (N, N, N), mode="ns", exponent=2.0)
+    assert torch.equal(out2, out)
+    # power-of-two feature scale
+    out2 = similarity_maps((fc * 4).contiguous(), pc, oc, (N, N, N), mode="ns", exponent=2.0)
+    assert torch.equal(out2, out)
+
+
 def test_legacy_similarity_matches_oracle():
     from oracle import similarity as osim, synth
     from vittf_b200 import infer

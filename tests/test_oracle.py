@@ -88,6 +88,17 @@ def test_ns_slabbed_equals_direct():
     assert torch.allclose(a, b, atol=2e-6)
 
 
+def test_ns_point_oracle_equals_slab_oracle():
+    feats, protos = synth.class_features(24, (6, 5, 4), 3, seed=2, dtype=torch.float16)
+    p = torch.cat([protos, protos.flip(0)])
+    offs = [0, 2, 4, 6]
+    for out_shape in ((24, 20, 16), (24, 15, 20), (48, 40, 32)):
+        ref = osim.ns_composite(feats, p, offs, out_shape, slab=4)
+        vox = torch.stack(torch.meshgrid(*[torch.arange(n) for n in out_shape], indexing="ij"), -1).reshape(-1, 3)
+        pts = osim.ns_at_voxels(feats, p, offs, out_shape, vox)
+        assert torch.allclose(pts, ref.reshape(3, -1), atol=3e-6)
+
+
 @pytest.mark.parametrize("name", ["bls_s755", "bls_s333", "bls_default"])
 def test_bls_matches_reference(golden, name):
     g = golden(name)
