@@ -117,3 +117,27 @@ def test_slab_sharded_solver_equals_single_pass():
             assert torch.equal(it.cpu(), it_ref.cpu())
         got = torch.cat(outs, dim=-1)
         assert (got - ref).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("n,n_rhs", [(256, 2), (512, 1)])
+def test_bls_full_size(n, n_rhs):
+    """BASELINE.json configs[4] sizes (256^3 and 512^3): the whole refined volume against the dense CPU oracle (1e-4, the
+    solver tolerance of the golden-vector tests), plus the size-independent properties of the solve: a constant target
+    is a fixed point, the solution is homogeneous of degree one in the target (PCG is; scale 0.5 is exact in binary)."""
+    from oracle import bls, synth
+    from vittf_b200.bilateral_solver3d import solve_many
+    shape = (n, n, n)
+    r8, lab = synth.ct_volume(shape, n_shells=8, seed=7)
+    gp = dict(sigma_spatial=7, sigma_luma=5, sigma_chroma=5)
+    gen = torch.Generator().manual_seed(3)
+    t = torch.stack([((lab == c + 1).float() * 0.8 + 0.2 * torch.rand(shape, generator=gen)).clamp(0, 1) for c in range(n_rhs)])
+    rc = r8.cuda()
+    out, iters = solve_many(t.cuda(), rc, None, gp)
+    for c in range(n_rhs):
+        ref, info = bls.solve_dense(t[c:c + 1], r8.expand(3, -1, -1, -1), grid_params=gp, return_info=True)
+        assert (out[c].cpu() - ref).abs().max().item() < 1e-4
+        assert int(iters[c]) == info["iters"]
+    half, _ = solve_many(t[:1].cuda() * 0.5, rc, None, gp)
+    assert (half[0] - 0.5 * out[0]).abs().max().item() < 1e-6
+    const, _ = solve_many(torch.full((1,) + shape, 0.625, device="cuda"), rc, None, gp)
+    assert (const[0] - 0.625).abs().max().item() < 1e-5
