@@ -125,6 +125,41 @@ def test_vit_full_depth_512(golden):
     assert (out - ref).abs().max().item() < 0.05 * ref.abs().max().item()
 
 
+def test_feature_volume_full_size_properties():
+    """BASELINE.json configs[1] (256^3 uint8, ViT-S/8, 12 blocks, 768 slice images of 512^2): size-independent properties of
+    stage 1 -- the feature volume does not depend on the slice batch size (bit-exact: slices are independent units), nor
+    on how the slices are sharded (two emulated ranks write disjoint slabs whose sum is the un-sharded volume, bit-exact),
+    every value is finite, and pooled slabs sampled along each axis match the fp32 CPU oracle on those slices (cos >= 0.995)."""
+    from oracle import dino_vit, feature_volume as fv, synth
+    from vittf_b200 import infer, ops
+    from vittf_b200.vit import engine_for
+    dev = torch.device("cuda", 0)
+    vol, _ = synth.ct_volume((256, 256, 256), n_shells=8, seed=0)
+    model = dino_vit.build("vits8", seed=0)
+    v = vol.to(dev)
+    a = infer.feature_volume(v, model, 8, 64, batch_size=64)
+    assert a.shape == (384, 64, 64, 64) and a.dtype == torch.float16 and torch.isfinite(a.float()).all()
+    b = infer.feature_volume(v, model, 8, 64, batch_size=24)
+    assert torch.equal(a, b)
+    # sharding: per axis the ranks' zero-initialised partial volumes have disjoint supports; their sum is the axis volume
+    im_sz, f_sz = infer.image_sizes((256, 256, 256), 8, 64)
+    eng = engine_for(model, dev, max_batch=32)
+    mm = ops.minmax(v)
+    acc = None
+    for ax in ["z", "y", "x"]:
+        parts = [infer.k_features_axis_device(v, eng, im_sz, ax, 32, 64, mm=mm, rank=r, world=2) for r in range(2)]
+        assert ((parts[0] != 0) & (parts[1] != 0)).sum().item() == 0
+        part = parts[0] + parts[1]
+        acc = part if acc is None else ops.accumulate_f16(acc, part)
+        if ax == "z":
+            # pooled slab 17 of the z pass = mean of slices 68..71: against the fp32 oracle on those four slices
+            imgs = F.interpolate(fv.slice_images(vol, "z")[68:72], size=(512, 512), mode="nearest")
+            ref = fv.hooked_qkv(model, imgs)[:, 1:, 384:768].float().mean(0)          # (4096, 384)
+            got = part[:, :, :, 17].float().reshape(384, -1).t().cpu()
+            assert F.cosine_similarity(got, ref, dim=-1).min().item() >= 0.995
+    assert torch.equal(acc, a)
+
+
 @pytest.mark.parametrize("arch,depth", [("vits16", 3), ("vitb16", 2), ("vitb8", 2)])
 def test_other_backbones_match_oracle(arch, depth):
     """--dino-model vits16 / vitb16 (patch 16: the 224^2 position grid is 14 x 14 and is always
