@@ -142,9 +142,26 @@ def cpu_reference(workload, budget_s=20.0):
 
 
 # --------------------------------------------------------------------------------------------- main
+_JSON_FD = None
+
+
+def _emit(obj):
+    """The ONE JSON line, written to the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner to stdout: rank 0 must print ONE JSON line
+    # NCCL (and anything else native) writes banners straight to file descriptor 1: keep the original stdout for the
+    # JSON line only and send every other write to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -174,7 +191,7 @@ def main():
         v = sum(x["value"] for x in vals) / len(vals)
         cb = dict(vals[-1])
         cb["value"] = v
-        print(json.dumps({"impl": "reference", "metric": "ms per volume end-to-end (ViT feats + similarity)", "value": v,
+        _emit(({"impl": "reference", "metric": "ms per volume end-to-end (ViT feats + similarity)", "value": v,
                           "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v,
                           "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "config": config, "cpu_baseline": cb,
@@ -182,7 +199,7 @@ def main():
         return 0
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: vittf_b200 has no CPU fallback"}))
+        _emit({"error": "no CUDA device: vittf_b200 has no CPU fallback"})
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -310,7 +327,7 @@ def main():
             out["cpu_baseline"] = cpu_reference(args.workload)
         except Exception as e:  # the baseline is a reported number; never let it hide the GPU result
             out["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(out))
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
