@@ -240,6 +240,15 @@ int vittf_mean_pairwise_distance(const float* feats, int N, int F, int measure, 
  * mask / out uint8 (W,H,D), non-zero = foreground; connectivity >= 3 is the full 3x3x3 box (:20-23). */
 int vittf_binary_erosion(const uint8_t* mask, int W, int H, int D, int connectivity, uint8_t* out, void* stream);
 
+/* =====================================================================================
+ * Evaluation (evaluate_similarities.py:58-83) -- SURVEY.md 8f row 3
+ * ===================================================================================== */
+/* sklearn.metrics.confusion_matrix of two uint8 label volumes (n voxels, values < K <= 16): out[t * K + p] = number of
+ * voxels with true label t and predicted label p (K*K uint64, zeroed by the call); out_of_range = voxels whose labels
+ * were >= K (counted nowhere).  precision / recall / F1 / Jaccard / accuracy (:66-71) derive from this table. */
+int vittf_confusion_matrix(const uint8_t* truth, const uint8_t* pred, int64_t n, int K, unsigned long long* out,
+                           unsigned int* out_of_range, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

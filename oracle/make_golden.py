@@ -174,5 +174,41 @@ def main():
     np.savez_compressed(OUT / "crop.npz", s=s.numpy(), c0=crops[0].numpy(), c1=crops[1].numpy(), mi=mi.numpy(), ma=ma.numpy())
 
 
+def golden_eval():
+    """tests/golden/eval_metrics.json = the metrics.json written by the UNMODIFIED /root/reference/evaluate_similarities.py
+    (run as a script; icecream stubbed: it only pretty-prints) for the seeded inputs of oracle.evaluate.make_inputs."""
+    import json
+    import runpy
+    import tempfile
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import evaluate as oev
+    ice = types.ModuleType("icecream")
+    ice.ic = lambda *a, **k: None
+    ice.ic.configureOutput = lambda **k: None
+
+    class _Reg:
+        @staticmethod
+        def register(_t):
+            return lambda f: f
+    ice.argumentToString = _Reg
+    sys.modules["icecream"] = ice
+    with tempfile.TemporaryDirectory() as tmp:
+        d, label_fn, names = oev.make_inputs(tmp, seed=0)
+        argv = sys.argv
+        sys.argv = ["evaluate_similarities.py", "--data", str(d), "--label", str(label_fn), "--labels", *names]
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                runpy.run_path(REF + "/evaluate_similarities.py", run_name="__main__")
+        finally:
+            sys.argv = argv
+        res = json.loads((d / "metrics.json").read_text())
+    (OUT / "eval_metrics.json").write_text(json.dumps(res, indent=1))
+    print("eval_metrics", {k: round(v["accuracy"], 4) for k, v in res.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":
+        golden_eval()
+    else:
+        main()

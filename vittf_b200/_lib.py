@@ -71,6 +71,7 @@ _SIGNATURES = {
     "vittf_binary_erosion": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "vittf_topk_voxels": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "vittf_mean_pairwise_distance": (_i, [_p, _i, _i, _i, _p, _p]),
+    "vittf_confusion_matrix": (_i, [_p, _p, _i64, _i, _p, _p, _p]),
     "vittf_bls_grid_cells": (_i64, [C.POINTER(BlsParams)]),
     "vittf_bls_grid_workspace_bytes": (_i64, [C.POINTER(BlsParams), _i]),
     "vittf_bls_sobel_slab": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),

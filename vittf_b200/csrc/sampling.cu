@@ -134,6 +134,49 @@ __global__ void __launch_bounds__(256) mean_distance_kernel(const float* __restr
 
 }  // namespace
 
+namespace {
+// ---------------------------------------------------------------------------------------------
+// evaluate_similarities.py:66-71: sklearn's confusion_matrix / precision / recall / F1 / Jaccard /
+// accuracy all derive from the K x K table of (true, predicted) label pairs, the only volume-sized work.  One pass over
+// the two uint8 volumes (2 B / voxel, HBM-bound): every thread keeps PRIVATE counters in shared memory
+// (s_cnt[pair][thread]: bank = thread, so neither atomics nor conflicts -- label volumes are long runs of one value, the
+// worst case for shared atomics), 16 voxels per 128-bit load; a warp shuffle tree folds the threads, one 64-bit atomic per
+// pair and CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void confusion_matrix_kernel(const uint8_t* __restrict__ truth, const uint8_t* __restrict__ pred, int64_t n, int K,
+                                        unsigned long long* __restrict__ out, unsigned int* __restrict__ out_of_range) {
+    extern __shared__ unsigned int s_cnt[];                 // [K * K][blockDim.x]
+    const int tid = threadIdx.x, nt = blockDim.x, KK = K * K;
+    for (int i = 0; i < KK; ++i) s_cnt[i * nt + tid] = 0;
+    unsigned int bad = 0;
+    auto count = [&](uint32_t t, uint32_t p) {
+        if (t < static_cast<uint32_t>(K) && p < static_cast<uint32_t>(K)) s_cnt[(t * K + p) * nt + tid] += 1;
+        else ++bad;
+    };
+    const int64_t n16 = ((reinterpret_cast<uintptr_t>(truth) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0 ? n / 16 : 0;
+    const uint4* t4 = reinterpret_cast<const uint4*>(truth);
+    const uint4* p4 = reinterpret_cast<const uint4*>(pred);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(nt) + tid; i < n16; i += static_cast<int64_t>(gridDim.x) * nt) {
+        const uint4 a = __ldg(t4 + i), b = __ldg(p4 + i);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) count((aw[wd] >> (8 * k)) & 255u, (bw[wd] >> (8 * k)) & 255u);
+    }
+    for (int64_t i = n16 * 16 + blockIdx.x * static_cast<int64_t>(nt) + tid; i < n; i += static_cast<int64_t>(gridDim.x) * nt)
+        count(truth[i], pred[i]);
+    // fold the threads: each warp reduces its 32 columns of every pair
+    for (int i = 0; i < KK; ++i) {
+        unsigned int v = s_cnt[i * nt + tid];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0 && v) atomicAdd(out + i, static_cast<unsigned long long>(v));
+    }
+    if (bad) atomicAdd(out_of_range, bad);
+}
+}  // namespace
+
 extern "C" int vittf_topk_voxels(const float* maps, int n_maps, int64_t n, int K, long long* out_idx, float* out_thr, void* stream) {
     VITTF_REQUIRE(maps && out_idx && n_maps > 0 && n > 0, "vittf_topk_voxels: bad arguments");
     VITTF_REQUIRE(K > 0 && K <= TOPK_MAX && K <= n, "vittf_topk_voxels: K=%d must be in [1, min(%d, n)]", K, TOPK_MAX);
@@ -160,6 +203,26 @@ extern "C" int vittf_binary_erosion(const uint8_t* mask, int W, int H, int D, in
     const int64_t cap = static_cast<int64_t>(vittf_num_sms()) * 16;
     if (blocks > cap) blocks = cap;
     binary_erosion_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, W, H, D, connectivity, out);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
+
+extern "C" int vittf_confusion_matrix(const uint8_t* truth, const uint8_t* pred, int64_t n, int K, unsigned long long* out,
+                                      unsigned int* out_of_range, void* stream) {
+    VITTF_REQUIRE(truth && pred && out && out_of_range && n > 0, "vittf_confusion_matrix: bad arguments");
+    VITTF_REQUIRE(K >= 1 && K <= 16, "vittf_confusion_matrix: K=%d must be in [1, 16]", K);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VITTF_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long) * K * K, s));
+    VITTF_CHECK_CUDA(cudaMemsetAsync(out_of_range, 0, sizeof(unsigned int), s));
+    // private counters: K * K * threads * 4 B of shared memory (<= 48 KB), at least one warp
+    int threads = 256;
+    while (threads > 32 && static_cast<size_t>(K) * K * threads * 4 > 48 * 1024) threads >>= 1;
+    int64_t blocks = ceil_div_ll(ceil_div_ll(n, 16), threads);
+    const int64_t cap = static_cast<int64_t>(vittf_num_sms()) * 8;
+    blocks = blocks < 1 ? 1 : blocks > cap ? cap : blocks;
+    confusion_matrix_kernel<<<static_cast<unsigned>(blocks), threads, static_cast<size_t>(K) * K * threads * 4, s>>>(
+        truth, pred, n, K, out, out_of_range);
     VITTF_CHECK_CUDA(cudaGetLastError());
     vittf_count_launches(1);
     return VITTF_OK;

@@ -277,3 +277,20 @@ def mean_pairwise_distance(feats, measure):
     check(load().vittf_mean_pairwise_distance(ptr(feats), N, F_, code, ptr(out), stream_ptr(feats.device)),
           "vittf_mean_pairwise_distance")
     return out
+
+
+def confusion_matrix(truth_u8, pred_u8, K):
+    """(K, K) int64 table of (true, predicted) label pairs of two uint8 CUDA tensors of equal size (rows = true labels,
+    as sklearn.metrics.confusion_matrix); labels >= K raise."""
+    require_cuda(truth_u8)
+    require_cuda(pred_u8)
+    if truth_u8.dtype != torch.uint8 or pred_u8.dtype != torch.uint8 or truth_u8.numel() != pred_u8.numel():
+        raise TypeError("confusion_matrix expects two uint8 tensors of the same size")
+    t, p = truth_u8.contiguous(), pred_u8.contiguous()
+    out = torch.empty(K * K, dtype=torch.int64, device=t.device)
+    bad = torch.empty(1, dtype=torch.int32, device=t.device)
+    check(load().vittf_confusion_matrix(ptr(t), ptr(p), t.numel(), int(K), ptr(out), ptr(bad), stream_ptr(t.device)),
+          "vittf_confusion_matrix")
+    if int(bad.item()) != 0:
+        raise ValueError(f"confusion_matrix: {int(bad.item())} voxels carry labels >= K={K}")
+    return out.view(K, K)
