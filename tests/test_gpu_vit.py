@@ -33,7 +33,8 @@ def test_layernorm(D):
 
 
 @pytest.mark.parametrize("axis", ["z", "y", "x"])
-@pytest.mark.parametrize("shape,n_out", [((8, 4, 6), 4), ((7, 4, 6), 3), ((6, 4, 6), 6)])
+@pytest.mark.parametrize("shape,n_out", [((8, 4, 6), 4), ((7, 4, 6), 3), ((6, 4, 6), 6), ((20, 5, 7), 8), ((64, 9, 5), 16),
+                                         ((37, 4, 9), 24)])
 def test_pool_axis_matches_adaptive_avg_pool(axis, shape, n_out):
     from vittf_b200 import ops
     S, f0, f1 = shape
@@ -48,6 +49,15 @@ def test_pool_axis_matches_adaptive_avg_pool(axis, shape, n_out):
     assert torch.equal(out, ref)
     acc = ops.pool_axis(k, f0, f1, axis, n_out, out=out.clone(), accumulate=True)
     assert torch.equal(acc, (ref + ref))
+    if n_out >= 16:
+        # sharded use: this "rank" holds only the slices of slabs [8, 12) and writes only those (partial 8-slab block)
+        lo, hi = (8 * S) // n_out, -((-12 * S) // n_out)
+        part = torch.zeros_like(out)
+        ops.pool_axis(k[lo:hi].contiguous(), f0, f1, axis, n_out, out=part, total_slices=S, slice0=lo, slabs=(8, 12))
+        sl = {"z": (..., slice(8, 12)), "y": (slice(None), slice(None), slice(8, 12)), "x": (slice(None), slice(8, 12))}[axis]
+        want = torch.zeros_like(ref)
+        want[sl] = ref[sl]
+        assert torch.equal(part, want)
 
 
 def _oracle_tokens(model, vol, axis, im_sz):
