@@ -3,6 +3,10 @@
 // accesses and grids that are multiples of the SM count.
 #include <float.h>
 
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -226,6 +230,175 @@ __global__ void __launch_bounds__(256) patch_embed_tiled_kernel(PatchParams q, i
                 for (int k = 0; k < 12; ++k) dst[32 * k] = acc[j][k];                              // 128 B per warp store
             }
         }
+    }
+}
+
+// Tensor-core variant for patch 8: per (image, patch row) the 64 x 64 (patch, tap) matrix of gathered grey values times
+// the folded (64 taps x 384 d) weight panel is a GEMM.  fp16 operands, fp32 accumulation (mma.sync m16n8k16): the grey
+// values g in [0, 1] lose <= 2^-12 absolute (a 16th of a uint8 step), the weights are split hi + lo (K = 128: [g | g] x
+// [W_hi ; W_lo]) so they enter at fp32 accuracy.  The panel lives in shared memory for the whole (persistent) kernel as
+// [d][k] rows padded to 272 B, the gathered tile as [patch][tap] rows of 144 B -- odd multiples of 16 B, so every ldmatrix
+// phase is bank-conflict free.  A warp owns 32 patches x 96 channels (2 x 12 accumulator tiles); the gather of the next
+// item overlaps the MMAs of the current one (two tile buffers).  The FMA-pipe kernel above took ~500 us per 64 slices
+// (37 % of the fp32 peak, 3.9 % of the ViT step); the output write (403 MB per 64 slices) is the floor here.
+constexpr int PM_WK = 136, PM_GK = 72;
+
+__device__ __forceinline__ void pm_ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void pm_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(PatchParams q, int n_imgs) {
+    extern __shared__ __align__(16) uint8_t pm_raw[];
+    __half* s_w = reinterpret_cast<__half*>(pm_raw);            // [384 d][136]: k 0..63 = W_hi[tap], 64..127 = W_lo[tap]
+    __half* s_g = s_w + PE_DCH * PM_WK;                         // [hi | lo][2 buffers][64 patches][72]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int d0 = blockIdx.y * PE_DCH;
+    // uint8 / fp16 volumes: the A operand is the RAW voxel value (exact in fp16); min-max normalisation moves into the
+    // weights (W' / (hi - lo), scaled by 2^e into fp16's normal range, undone in the epilogue) and the bias
+    // (b' - lo / (hi - lo) * sum_taps W').  fp32 volumes: A = fp16((v - lo) / (hi - lo)), <= 2^-12 absolute.
+    constexpr bool RAW = !std::is_same<T, float>::value;
+    const float lo = q.minmax[0], inv = 1.0f / (q.minmax[1] - q.minmax[0]);
+    int sexp = 0;
+    if (RAW) frexpf(q.minmax[1] - q.minmax[0], &sexp);                     // hi - lo = m 2^e, m in [0.5, 1)
+    const float wscale = RAW ? ldexpf(inv, sexp) : 1.0f, oscale = RAW ? ldexpf(1.0f, -sexp) : 1.0f;
+    for (int i = tid; i < PE_TAPS * PE_DCH; i += 256) {
+        const int t = i / PE_DCH, n = i - t * PE_DCH;
+        const float v = q.w[static_cast<size_t>(t) * q.D + d0 + n] * wscale;
+        const __half hi = __float2half_rn(v);
+        s_w[n * PM_WK + t] = hi;
+        s_w[n * PM_WK + PE_TAPS + t] = __float2half_rn(v - __half2float(hi));
+    }
+    // column sums of the folded weights (fixed summation order: identical in every CTA and launch)
+    float* s_cs = reinterpret_cast<float*>(s_g + 4 * PE_PX * PM_GK);
+    if (RAW) {
+        for (int n = tid; n < PE_DCH; n += 256) {
+            float cs = 0.0f;
+#pragma unroll 16
+            for (int tp = 0; tp < PE_TAPS; ++tp) cs += q.w[static_cast<size_t>(tp) * q.D + d0 + n];
+            s_cs[n] = cs;
+        }
+        __syncthreads();
+    }
+    const int ntok = 1 + q.f0 * q.f1;
+    // CLS tokens: cls + pos[0] (row 0 of the pos table)
+    for (int i = blockIdx.x * 256 + tid; i < n_imgs * PE_DCH; i += gridDim.x * 256) {
+        const int img = i / PE_DCH, d = i - img * PE_DCH;
+        q.out[static_cast<size_t>(img) * ntok * q.D + d0 + d] = q.pos[d0 + d];
+    }
+    const float sc0 = static_cast<float>(q.a) / static_cast<float>(q.im0);
+    const float sc1 = static_cast<float>(q.b) / static_cast<float>(q.im1);
+    const T* vol = static_cast<const T*>(q.vol);
+    const int chunks = (q.f1 + PE_PX - 1) / PE_PX;
+    const int n_items = n_imgs * q.f0 * chunks;
+
+    // gather: one warp instruction = the 64 taps of one patch (lane = tap pair), 8 patches per warp
+    auto gather = [&](int item, __half* dst) {
+        const int pxc = item % chunks, py = (item / chunks) % q.f0, img = item / (chunks * q.f0);
+        const int s = q.s0 + img;
+        const int u = lane >> 2, v = (lane & 3) * 2;                       // taps (u, v) and (u, v + 1)
+        const int r = nearest_src(py * 8 + u, q.a, q.im0, sc0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int pl = wid * 8 + j, px = pxc * PE_PX + pl;
+            float g0 = 0.0f, g1 = 0.0f;
+            if (px < q.f1) {
+                const int c0 = nearest_src(px * 8 + v, q.b, q.im1, sc1), c1 = nearest_src(px * 8 + v + 1, q.b, q.im1, sc1);
+                int64_t i0, i1;
+                if (q.axis == 2) { i0 = (static_cast<int64_t>(r) * q.Y + c0) * q.Z + s; i1 = (static_cast<int64_t>(r) * q.Y + c1) * q.Z + s; }
+                else if (q.axis == 1) { i0 = (static_cast<int64_t>(r) * q.Y + s) * q.Z + c0; i1 = i0 + (c1 - c0); }
+                else { i0 = (static_cast<int64_t>(s) * q.Y + r) * q.Z + c0; i1 = i0 + (c1 - c0); }
+                g0 = load_as_float<T>(vol, i0);
+                g1 = load_as_float<T>(vol, i1);
+                if (!RAW) {
+                    g0 = (g0 - lo) * inv;
+                    g1 = (g1 - lo) * inv;
+                }
+            }
+            const __half2 gh = __floats2half2_rn(g0, g1);
+            *reinterpret_cast<__half2*>(dst + pl * PM_GK + 2 * lane) = gh;
+            if (!RAW) {                                   // residual tile: fp32 volumes enter as g_hi + g_lo
+                const float2 back = __half22float2(gh);
+                *reinterpret_cast<__half2*>(dst + 2 * PE_PX * PM_GK + pl * PM_GK + 2 * lane) = __floats2half2_rn(g0 - back.x, g1 - back.y);
+            }
+        }
+    };
+
+    const int mh = wid & 1, nq = wid >> 1;                 // patches [32 mh, +32), channels [96 nq, +96) of the chunk
+    const int g = lane >> 2, t = lane & 3, mi = lane >> 3, mr = lane & 7;
+    const uint32_t a_lane = ((32 * mh + (mi & 1) * 8 + mr) * PM_GK + (mi >> 1) * 8) * 2;      // + 16 mt rows, + 16 ks cols
+    const uint32_t b_lane = ptx::smem_u32(s_w) + ((96 * nq + (mi >> 1) * 8 + mr) * PM_WK + (mi & 1) * 8) * 2;
+    float bias[12][2];
+#pragma unroll
+    for (int j = 0; j < 12; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int d = d0 + 96 * nq + 8 * j + 2 * t + e;
+            bias[j][e] = q.bias[d] - (RAW ? lo * inv * s_cs[d - d0] : 0.0f);
+        }
+    int buf = 0;
+    if (blockIdx.x < n_items) gather(blockIdx.x, s_g);
+    __syncthreads();
+    const float iscale = 1.0f / oscale;                    // (powers of two: exact)
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        // the accumulators start as (bias + pos-embed) 2^e: these loads land straight in the accumulator registers and
+        // are in flight while the next item is gathered
+        const int pxc = item % chunks, py = (item / chunks) % q.f0, img = item / (chunks * q.f0);
+        float acc[2][12][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int px = pxc * PE_PX + 32 * mh + 16 * m + g + 8 * h;
+                const size_t tok = 1 + static_cast<size_t>(py) * q.f1 + (px < q.f1 ? px : 0);
+                const float* pos = q.pos + tok * q.D + d0 + 96 * nq + 2 * t;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    const float2 pe = __ldg(reinterpret_cast<const float2*>(pos + 8 * j));
+                    acc[m][j][2 * h] = (pe.x + bias[j][0]) * iscale;
+                    acc[m][j][2 * h + 1] = (pe.y + bias[j][1]) * iscale;
+                }
+            }
+        if (item + gridDim.x < n_items) gather(item + gridDim.x, s_g + (buf ^ 1) * PE_PX * PM_GK);
+        const uint32_t ga = ptx::smem_u32(s_g + buf * PE_PX * PM_GK) + a_lane;
+        // k-steps 0..3: g x W_hi, 4..7: g x W_lo, (fp32 volumes) 8..11: g_lo x W_hi
+#pragma unroll
+        for (int kk = 0; kk < (RAW ? 8 : 12); ++kk) {
+            uint32_t a0[4], a1[4];
+            const uint32_t gk = ga + (kk >= 8 ? 2 * PE_PX * PM_GK * 2 : 0) + (kk & 3) * 32;
+            pm_ldmatrix_x4(gk, a0);
+            pm_ldmatrix_x4(gk + 16 * PM_GK * 2, a1);
+#pragma unroll
+            for (int jp = 0; jp < 6; ++jp) {
+                uint32_t bf[4];
+                pm_ldmatrix_x4(b_lane + (16 * jp * PM_WK + 16 * (kk >= 8 ? kk - 8 : kk)) * 2, bf);
+                pm_mma(acc[0][2 * jp], a0, bf[0], bf[1]);
+                pm_mma(acc[1][2 * jp], a1, bf[0], bf[1]);
+                pm_mma(acc[0][2 * jp + 1], a0, bf[2], bf[3]);
+                pm_mma(acc[1][2 * jp + 1], a1, bf[2], bf[3]);
+            }
+        }
+        // epilogue: undo the 2^e scale, fp32 tokens (float2 = a full 32-byte sector per row and quad)
+        float* out_img = q.out + static_cast<size_t>(img) * ntok * q.D;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int px = pxc * PE_PX + 32 * mh + 16 * m + g + 8 * h;
+                if (px >= q.f1) continue;
+                const size_t tok = 1 + static_cast<size_t>(py) * q.f1 + px;
+                float* dst = out_img + tok * q.D + d0 + 96 * nq + 2 * t;
+#pragma unroll
+                for (int j = 0; j < 12; ++j)
+                    *reinterpret_cast<float2*>(dst + 8 * j) = make_float2(acc[m][j][2 * h] * oscale, acc[m][j][2 * h + 1] * oscale);
+            }
+        __syncthreads();
+        buf ^= 1;
     }
 }
 
@@ -482,6 +655,33 @@ extern "C" int vittf_patch_embed(const void* vol, int vol_dtype, int X, int Y, i
     q.im0 = im0; q.im1 = im1; q.p = patch; q.D = D; q.f0 = im0 / patch; q.f1 = im1 / patch;
     q.minmax = minmax2; q.w = patch_w; q.bias = patch_b; q.pos = pos_embed; q.out = out_tokens;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    static const bool pe_no_mma = getenv("VITTF_PE_NO_MMA") != nullptr;     // A/B switch: FMA-pipe tiled kernel
+    if (patch == 8 && D % PE_DCH == 0 && !pe_no_mma) {   // tensor-core persistent kernel (patch-8 backbones)
+        const size_t smem_m = (static_cast<size_t>(PE_DCH) * PM_WK + 4 * PE_PX * PM_GK) * sizeof(__half) + PE_DCH * sizeof(float);
+        const int n_imgs = s1 - s0;
+        const int n_items = n_imgs * q.f0 * ((q.f1 + PE_PX - 1) / PE_PX);
+        dim3 grid_m(n_items < vittf_num_sms() ? n_items : vittf_num_sms(), D / PE_DCH);
+#define LAUNCH_PEM(T)                                                                                                   \
+    do {                                                                                                                \
+        static bool configured = false;                                                                                 \
+        if (!configured) {                                                                                              \
+            VITTF_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                  static_cast<int>(smem_m)));                                          \
+            configured = true;                                                                                          \
+        }                                                                                                               \
+        patch_embed_mma_kernel<T><<<grid_m, 256, smem_m, s>>>(q, n_imgs);                                               \
+    } while (0)
+        switch (vol_dtype) {
+            case VITTF_U8: LAUNCH_PEM(uint8_t); break;
+            case VITTF_F16: LAUNCH_PEM(__half); break;
+            case VITTF_F32: LAUNCH_PEM(float); break;
+            default: VITTF_REQUIRE(false, "vittf_patch_embed: unsupported volume dtype %d", vol_dtype);
+        }
+#undef LAUNCH_PEM
+        VITTF_CHECK_CUDA(cudaGetLastError());
+        vittf_count_launches(1);
+        return VITTF_OK;
+    }
     if (patch == 8 && D % PE_DCH == 0) {        // register-tiled persistent kernel (patch-8 backbones)
         const size_t smem_t = static_cast<size_t>(PE_TAPS) * (PE_DCH + PE_PX) * sizeof(float);
         const int n_items = (s1 - s0) * (q.f0 + 1);
