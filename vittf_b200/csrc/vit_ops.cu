@@ -238,10 +238,10 @@ __global__ void __launch_bounds__(256) patch_embed_tiled_kernel(PatchParams q, i
 // values g in [0, 1] lose <= 2^-12 absolute (a 16th of a uint8 step), the weights are split hi + lo (K = 128: [g | g] x
 // [W_hi ; W_lo]) so they enter at fp32 accuracy.  The panel lives in shared memory for the whole (persistent) kernel as
 // [d][k] rows padded to 272 B, the gathered tile as [patch][tap] rows of 144 B -- odd multiples of 16 B, so every ldmatrix
-// phase is bank-conflict free.  A warp owns 32 patches x 96 channels (2 x 12 accumulator tiles); the gather of the next
+// phase is bank-conflict free.  16 warps, each 16 patches x 96 channels (12 accumulator tiles); the gather of the next
 // item overlaps the MMAs of the current one (two tile buffers).  The FMA-pipe kernel above took ~500 us per 64 slices
 // (37 % of the fp32 peak, 3.9 % of the ViT step); the output write (403 MB per 64 slices) is the floor here.
-constexpr int PM_WK = 136, PM_GK = 72;
+constexpr int PM_WK = 136, PM_GK = 72, PM_WARPS = 16, PM_THREADS = 32 * PM_WARPS;
 
 __device__ __forceinline__ void pm_ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -253,7 +253,7 @@ __device__ __forceinline__ void pm_mma(float (&d)[4], const uint32_t (&a)[4], ui
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(PatchParams q, int n_imgs) {
+__global__ void __launch_bounds__(PM_THREADS, 1) patch_embed_mma_kernel(PatchParams q, int n_imgs) {
     extern __shared__ __align__(16) uint8_t pm_raw[];
     __half* s_w = reinterpret_cast<__half*>(pm_raw);            // [384 d][136]: k 0..63 = W_hi[tap], 64..127 = W_lo[tap]
     __half* s_g = s_w + PE_DCH * PM_WK;                         // [hi | lo][2 buffers][64 patches][72]
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(PatchParams q, 
     int sexp = 0;
     if (RAW) frexpf(q.minmax[1] - q.minmax[0], &sexp);                     // hi - lo = m 2^e, m in [0.5, 1)
     const float wscale = RAW ? ldexpf(inv, sexp) : 1.0f, oscale = RAW ? ldexpf(1.0f, -sexp) : 1.0f;
-    for (int i = tid; i < PE_TAPS * PE_DCH; i += 256) {
+    for (int i = tid; i < PE_TAPS * PE_DCH; i += PM_THREADS) {
         const int t = i / PE_DCH, n = i - t * PE_DCH;
         const float v = q.w[static_cast<size_t>(t) * q.D + d0 + n] * wscale;
         const __half hi = __float2half_rn(v);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(PatchParams q, 
     // column sums of the folded weights (fixed summation order: identical in every CTA and launch)
     float* s_cs = reinterpret_cast<float*>(s_g + 4 * PE_PX * PM_GK);
     if (RAW) {
-        for (int n = tid; n < PE_DCH; n += 256) {
+        for (int n = tid; n < PE_DCH; n += PM_THREADS) {
             float cs = 0.0f;
 #pragma unroll 16
             for (int tp = 0; tp < PE_TAPS; ++tp) cs += q.w[static_cast<size_t>(tp) * q.D + d0 + n];
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(PatchParams q, 
     }
     const int ntok = 1 + q.f0 * q.f1;
     // CLS tokens: cls + pos[0] (row 0 of the pos table)
-    for (int i = blockIdx.x * 256 + tid; i < n_imgs * PE_DCH; i += gridDim.x * 256) {
+    for (int i = blockIdx.x * PM_THREADS + tid; i < n_imgs * PE_DCH; i += gridDim.x * PM_THREADS) {
         const int img = i / PE_DCH, d = i - img * PE_DCH;
         q.out[static_cast<size_t>(img) * ntok * q.D + d0 + d] = q.pos[d0 + d];
     }
@@ -297,15 +297,15 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(PatchParams q, 
     const int chunks = (q.f1 + PE_PX - 1) / PE_PX;
     const int n_items = n_imgs * q.f0 * chunks;
 
-    // gather: one warp instruction = the 64 taps of one patch (lane = tap pair), 8 patches per warp
+    // gather: one warp instruction = the 64 taps of one patch (lane = tap pair), 4 patches per warp
     auto gather = [&](int item, __half* dst) {
         const int pxc = item % chunks, py = (item / chunks) % q.f0, img = item / (chunks * q.f0);
         const int s = q.s0 + img;
         const int u = lane >> 2, v = (lane & 3) * 2;                       // taps (u, v) and (u, v + 1)
         const int r = nearest_src(py * 8 + u, q.a, q.im0, sc0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int pl = wid * 8 + j, px = pxc * PE_PX + pl;
+        for (int j = 0; j < PE_PX / PM_WARPS; ++j) {
+            const int pl = wid * (PE_PX / PM_WARPS) + j, px = pxc * PE_PX + pl;
             float g0 = 0.0f, g1 = 0.0f;
             if (px < q.f1) {
                 const int c0 = nearest_src(px * 8 + v, q.b, q.im1, sc1), c1 = nearest_src(px * 8 + v + 1, q.b, q.im1, sc1);
@@ -329,9 +329,9 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(PatchParams q, 
         }
     };
 
-    const int mh = wid & 1, nq = wid >> 1;                 // patches [32 mh, +32), channels [96 nq, +96) of the chunk
+    const int mq = wid & 3, nq = wid >> 2;                 // patches [16 mq, +16), channels [96 nq, +96) of the chunk
     const int g = lane >> 2, t = lane & 3, mi = lane >> 3, mr = lane & 7;
-    const uint32_t a_lane = ((32 * mh + (mi & 1) * 8 + mr) * PM_GK + (mi >> 1) * 8) * 2;      // + 16 mt rows, + 16 ks cols
+    const uint32_t a_lane = ((16 * mq + (mi & 1) * 8 + mr) * PM_GK + (mi >> 1) * 8) * 2;      // + 16 ks cols
     const uint32_t b_lane = ptx::smem_u32(s_w) + ((96 * nq + (mi >> 1) * 8 + mr) * PM_WK + (mi & 1) * 8) * 2;
     float bias[12][2];
 #pragma unroll
@@ -349,54 +349,46 @@ __global__ void __launch_bounds__(256, 1) patch_embed_mma_kernel(PatchParams q, 
         // the accumulators start as (bias + pos-embed) 2^e: these loads land straight in the accumulator registers and
         // are in flight while the next item is gathered
         const int pxc = item % chunks, py = (item / chunks) % q.f0, img = item / (chunks * q.f0);
-        float acc[2][12][4];
+        float acc[12][4];
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int h = 0; h < 2; ++h) {
+            const int px = pxc * PE_PX + 16 * mq + g + 8 * h;
+            const size_t tok = 1 + static_cast<size_t>(py) * q.f1 + (px < q.f1 ? px : 0);
+            const float* pos = q.pos + tok * q.D + d0 + 96 * nq + 2 * t;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int px = pxc * PE_PX + 32 * mh + 16 * m + g + 8 * h;
-                const size_t tok = 1 + static_cast<size_t>(py) * q.f1 + (px < q.f1 ? px : 0);
-                const float* pos = q.pos + tok * q.D + d0 + 96 * nq + 2 * t;
-#pragma unroll
-                for (int j = 0; j < 12; ++j) {
-                    const float2 pe = __ldg(reinterpret_cast<const float2*>(pos + 8 * j));
-                    acc[m][j][2 * h] = (pe.x + bias[j][0]) * iscale;
-                    acc[m][j][2 * h + 1] = (pe.y + bias[j][1]) * iscale;
-                }
+            for (int j = 0; j < 12; ++j) {
+                const float2 pe = __ldg(reinterpret_cast<const float2*>(pos + 8 * j));
+                acc[j][2 * h] = (pe.x + bias[j][0]) * iscale;
+                acc[j][2 * h + 1] = (pe.y + bias[j][1]) * iscale;
             }
+        }
         if (item + gridDim.x < n_items) gather(item + gridDim.x, s_g + (buf ^ 1) * PE_PX * PM_GK);
         const uint32_t ga = ptx::smem_u32(s_g + buf * PE_PX * PM_GK) + a_lane;
         // k-steps 0..3: g x W_hi, 4..7: g x W_lo, (fp32 volumes) 8..11: g_lo x W_hi
 #pragma unroll
         for (int kk = 0; kk < (RAW ? 8 : 12); ++kk) {
-            uint32_t a0[4], a1[4];
-            const uint32_t gk = ga + (kk >= 8 ? 2 * PE_PX * PM_GK * 2 : 0) + (kk & 3) * 32;
-            pm_ldmatrix_x4(gk, a0);
-            pm_ldmatrix_x4(gk + 16 * PM_GK * 2, a1);
+            uint32_t a0[4];
+            pm_ldmatrix_x4(ga + (kk >= 8 ? 2 * PE_PX * PM_GK * 2 : 0) + (kk & 3) * 32, a0);
 #pragma unroll
             for (int jp = 0; jp < 6; ++jp) {
                 uint32_t bf[4];
                 pm_ldmatrix_x4(b_lane + (16 * jp * PM_WK + 16 * (kk >= 8 ? kk - 8 : kk)) * 2, bf);
-                pm_mma(acc[0][2 * jp], a0, bf[0], bf[1]);
-                pm_mma(acc[1][2 * jp], a1, bf[0], bf[1]);
-                pm_mma(acc[0][2 * jp + 1], a0, bf[2], bf[3]);
-                pm_mma(acc[1][2 * jp + 1], a1, bf[2], bf[3]);
+                pm_mma(acc[2 * jp], a0, bf[0], bf[1]);
+                pm_mma(acc[2 * jp + 1], a0, bf[2], bf[3]);
             }
         }
         // epilogue: undo the 2^e scale, fp32 tokens (float2 = a full 32-byte sector per row and quad)
         float* out_img = q.out + static_cast<size_t>(img) * ntok * q.D;
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int h = 0; h < 2; ++h) {
+            const int px = pxc * PE_PX + 16 * mq + g + 8 * h;
+            if (px >= q.f1) continue;
+            const size_t tok = 1 + static_cast<size_t>(py) * q.f1 + px;
+            float* dst = out_img + tok * q.D + d0 + 96 * nq + 2 * t;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int px = pxc * PE_PX + 32 * mh + 16 * m + g + 8 * h;
-                if (px >= q.f1) continue;
-                const size_t tok = 1 + static_cast<size_t>(py) * q.f1 + px;
-                float* dst = out_img + tok * q.D + d0 + 96 * nq + 2 * t;
-#pragma unroll
-                for (int j = 0; j < 12; ++j)
-                    *reinterpret_cast<float2*>(dst + 8 * j) = make_float2(acc[m][j][2 * h] * oscale, acc[m][j][2 * h + 1] * oscale);
-            }
+            for (int j = 0; j < 12; ++j)
+                *reinterpret_cast<float2*>(dst + 8 * j) = make_float2(acc[j][2 * h] * oscale, acc[j][2 * h + 1] * oscale);
+        }
         __syncthreads();
         buf ^= 1;
     }
@@ -669,7 +661,7 @@ extern "C" int vittf_patch_embed(const void* vol, int vol_dtype, int X, int Y, i
                                                   static_cast<int>(smem_m)));                                          \
             configured = true;                                                                                          \
         }                                                                                                               \
-        patch_embed_mma_kernel<T><<<grid_m, 256, smem_m, s>>>(q, n_imgs);                                               \
+        patch_embed_mma_kernel<T><<<grid_m, PM_THREADS, smem_m, s>>>(q, n_imgs);                                               \
     } while (0)
         switch (vol_dtype) {
             case VITTF_U8: LAUNCH_PEM(uint8_t); break;
