@@ -81,7 +81,11 @@ def test_compute_similarities_with_bilateral_solver(golden):
                                                ((8, 8, 8), (8, 8, 8), 32, 3), ((12, 10, 8), (31, 29, 17), 40, 20),
                                                ((8, 8, 8), (16, 16, 16), 32, 5), ((8, 8, 8), (64, 64, 64), 48, 9),
                                                ((33, 33, 33), (132, 132, 132), 16, 4), ((6, 5, 4), (24, 20, 16), 24, 7),
-                                               ((5, 4, 6), (40, 32, 48), 32, 12), ((32, 32, 32), (128, 128, 128), 64, 32)])
+                                               ((5, 4, 6), (40, 32, 48), 32, 12), ((32, 32, 32), (128, 128, 128), 64, 32),
+                                               # fused tensor-core pass 1 (F % 32 == 0, d % 8 == 0) at awkward extents: odd h,
+                                               # d below / not a multiple of the 64-voxel z tile, more than 32 prototypes
+                                               ((5, 7, 16), (20, 28, 64), 32, 9), ((6, 5, 24), (24, 20, 96), 64, 40),
+                                               ((3, 3, 72), (12, 12, 288), 32, 5), ((9, 6, 8), (72, 48, 64), 96, 33)])
 def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
     from oracle import similarity as osim, synth
     from vittf_b200.similarity import similarity_maps
