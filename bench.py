@@ -294,9 +294,16 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"
     att_ms, att_n = timing["attention"]
     d, l, h, _ = ARCH[arch]
-    att_flops_per_launch = 4.0 * batch * h * tokens * tokens * 64            # QK^T + PV, per launch of `batch` images
+    # QK^T + PV of every (image, layer) this rank ran in the timed steps, over the summed duration of its attention launches
+    # (a launch holds `batch` images only when the rank's slices per axis are a multiple of it)
+    from vittf_b200 import dist as vdist
+    local_imgs = 0
+    for ax_len, n_out in zip(vol.shape, f_sz):
+        a, b = vdist.slices_for_slabs(int(ax_len), int(n_out), *vdist.slab_range(int(n_out), world, rank))
+        local_imgs += b - a
+    att_flops_timed = 4.0 * h * tokens * tokens * 64 * local_imgs * (l - 1) * args.steps
     att_avg_ms = att_ms / max(1, att_n)
-    achieved = att_flops_per_launch / (att_avg_ms * 1e-3) / 1e12 if att_n else None
+    achieved = att_flops_timed / (att_ms * 1e-3) / 1e12 if att_n else None
     gemm_ms, gemm_n = timing["gemm"]
     n_img = 3 * size
     total_flops = needed_flops_per_image(arch, tokens) * n_img
