@@ -1336,7 +1336,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
     const int kz0 = U == 4 ? 2 * (t & 1) : 2 * t;
     const int ky_t = U == 4 ? (t >> 1) : 0;          // thread's fixed part of ky (U == 4: ky = 2 (j & 1) + (t >> 1))
     bool zok[2][2];
-    int oyb[2];
+    int oyb[2], ycl[2][2], zcl[2][2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         int id = tile * 16 + g + 8 * r;
@@ -1354,8 +1354,34 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
         zok[r][1] = rlive && oz + 1 >= q.z0 && oz + 1 < q.z1 && oz + 1 >= 0 && oz + 1 < q.D;
         oyb[r] = U * cy + U / 2 + ky_t;
         obase[r] = (oxb * q.H + oyb[r]) * zs + (oz - q.z0);
+        ycl[r][0] = y0c;
+        ycl[r][1] = y1c;
+        zcl[r][0] = z0c;
+        zcl[r][1] = z1c;
+    }
+    // the corner dots of the first UP_PD prototypes go out BEFORE the Gram phase: their L2 round trip overlaps the Gram
+    // loads and the norm arithmetic below
+    // (prototypes a + 1 .. a + UP_PD are in flight while a runs on the tensor cores: the loads are L2 hits, ~1 us away)
+    const float* da = q.dots;
+    const float* const da_last = q.dots + static_cast<size_t>(q.A - 1) * n_lr;
+    float nv[UP_PD][4];
+    // (volatile: the load must stay behind the consumption of the ring slot it refills, or the compiler loads into a
+    // temporary and copies it into the slot -- a copy that waits for the load)
+    auto ldv = [](const float* p) { float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; };
+    auto fetch = [&](float (&v)[4]) {
+        v[0] = ldv(up_ptr_at(da, off[0][0]));
+        v[1] = ldv(up_ptr_at(da, off[0][1]));
+        v[2] = ldv(up_ptr_at(da, off[1][0]));
+        v[3] = ldv(up_ptr_at(da, off[1][1]));
+        da = da < da_last ? da + n_lr : da;                              // (past the end: re-read the last prototype)
+    };
+#pragma unroll
+    for (int i = 0; i < UP_PD; ++i) fetch(nv[i]);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
         // Gram of the 8 corners -> contract z for the thread's two kz.  Distinct corners differ by exactly the cell's
         // clamped extents (ex, ey, ez in {0, 1}); the slot of a pair is looked up from those.
+        const int y0c = ycl[r][0], y1c = ycl[r][1], z0c = zcl[r][0], z1c = zcl[r][1];
         const int ex = x1c - x0c, ey = y1c - y0c, ez = z1c - z0c;
         const uint32_t base = (static_cast<uint32_t>(x0c) * h + y0c) * d + z0c;
         const uint32_t sx = ex ? static_cast<uint32_t>(h) * d : 0u, sy = ey ? static_cast<uint32_t>(d) : 0u, sz = ez ? 1u : 0u;
@@ -1434,24 +1460,6 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
     }
     // warp-uniform: every pair is stored whole (or not at all) as one 8-byte word
     const bool fast_st = __all_sync(0xffffffffu, vec_ok && m0 == m1);
-
-    // dots of the first prototype (software pipeline: prototype a + 1 is in flight while a runs on the tensor cores)
-    // (prototypes a + 1 .. a + UP_PD are in flight while a runs on the tensor cores: the loads are L2 hits, ~1 us away)
-    const float* da = q.dots;
-    const float* const da_last = q.dots + static_cast<size_t>(q.A - 1) * n_lr;
-    float nv[UP_PD][4];
-    // (volatile: the load must stay behind the consumption of the ring slot it refills, or the compiler loads into a
-    // temporary and copies it into the slot -- a copy that waits for the load)
-    auto ldv = [](const float* p) { float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; };
-    auto fetch = [&](float (&v)[4]) {
-        v[0] = ldv(up_ptr_at(da, off[0][0]));
-        v[1] = ldv(up_ptr_at(da, off[0][1]));
-        v[2] = ldv(up_ptr_at(da, off[1][0]));
-        v[3] = ldv(up_ptr_at(da, off[1][1]));
-        da = da < da_last ? da + n_lr : da;                              // (past the end: re-read the last prototype)
-    };
-#pragma unroll
-    for (int i = 0; i < UP_PD; ++i) fetch(nv[i]);
 
 #pragma unroll 1
     for (int sub = 0; sub < NSUB; ++sub) {
