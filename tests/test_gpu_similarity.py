@@ -158,6 +158,25 @@ def test_ns_similarity_full_size(F_, n, N, A, C):
     assert torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("lr,out_shape", [((8, 8, 8), (32, 32, 32)), ((8, 8, 8), (64, 64, 64)), ((6, 5, 4), (24, 15, 20))])
+def test_ns_similarity_with_empty_classes(lr, out_shape):
+    """A class without annotations is a zero map (max over nothing -> clamp), in the tensor-core and the generic kernels;
+    the other classes are unaffected."""
+    from oracle import similarity as osim, synth
+    from vittf_b200.similarity import similarity_maps
+    feats, protos = synth.class_features(32, lr, 3, seed=2, dtype=torch.float16)
+    g = torch.Generator().manual_seed(3)
+    p = F.normalize(protos[torch.tensor([0, 0, 0, 2, 2])] + 0.05 * torch.randn(5, 32, generator=g), dim=-1)
+    offs = [0, 0, 3, 3, 5, 5]                                           # classes 0, 2 and 4 are empty
+    out = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
+                          out_shape, mode="ns", exponent=2.0).cpu()
+    ref = osim.ns_composite(feats, p, [0, 3, 5], out_shape, exponent=2.0, slab=8)
+    assert out.shape[0] == 5
+    for c in (0, 2, 4):
+        assert torch.count_nonzero(out[c]).item() == 0
+    assert (out[1] - ref[0]).abs().max().item() < TOL and (out[3] - ref[1]).abs().max().item() < TOL
+
+
 def test_legacy_similarity_matches_oracle():
     from oracle import similarity as osim, synth
     from vittf_b200 import infer

@@ -1518,6 +1518,23 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
         };
         int c = 0, a_begin = 0, a_end = s_off[1];
         float* oc = q.out;
+        // classes without prototypes (max over nothing = -inf -> clamp -> 0, as the generic kernel): zero planes
+        auto skip_empty = [&]() {
+            while (c < q.C && a_end == a_begin) {
+#pragma unroll
+                for (int rj = 0; rj < 16; ++rj) {                       // (static indices: obase must stay in registers)
+                    const int r = rj >> 3, j = rj & 7;
+                    const int joff = U == 4 ? (j >> 1) * Hzs + 2 * (j & 1) * zs : sub * Hzs + j * zs;
+                    float* dst = up_out_at(oc, obase[r] + joff);
+                    if ((ms0 >> rj) & 1) dst[0] = 0.0f;
+                    if ((ms1 >> rj) & 1) dst[1] = 0.0f;
+                }
+                ++c;
+                oc += n_out;
+                a_end = c < q.C ? s_off[c + 1] : -1;
+            }
+        };
+        skip_empty();
         // flat loop over all prototypes, unrolled by the prefetch distance so that the ring of in-flight corner dots is
         // indexed statically (a register copy of a value still in flight would wait for it)
 #pragma unroll 1
@@ -1582,6 +1599,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
                 oc += n_out;
                 a_begin = a_end;
                 a_end = c < q.C ? s_off[c + 1] : -1;
+                skip_empty();
             }
         }
     }
