@@ -178,6 +178,12 @@ int vittf_sim_upsample(const float* dots, const float* gram, int w, int h, int d
 
 /* 0.99*max quantisation input (predict_ntf.py:95): per-class maximum, out fp32 (C) */
 int vittf_class_max(const float* sims, int C, int64_t n, float* out, void* stream);
+/* uint8 maps as compute_similarities returns them (predict_ntf.py:95-100): per class (255 / (0.99*class_max[c]) * sim) cast
+ * to uint8 with the C-style wrap of the reference's CPU cast, then F.interpolate(mode='nearest') to (Wo,Ho,Do).
+ * sims fp32 (C, W, H, z1-z0) is the z-slab [z0,z1) of a (W,H,D) grid; out uint8 (C, Wo, Ho, zo1-zo0) holds the output planes
+ * [zo0,zo1), whose source planes min(floor(oz*D/Do), D-1) must lie inside the slab.  class_max: device, fp32 (C). */
+int vittf_quantize_maps_u8(const float* sims, int C, int W, int H, int D, int z0, int z1, const float* class_max,
+                           int Wo, int Ho, int Do, int zo0, int zo1, uint8_t* out, void* stream);
 /* label composition (predict_ntf.py:203-215): thresholded running arg-max with strict '>'
  * on uint8 maps; thresholds_u8[i] = int(thr_i*255).  mode 1 = plain argmax(0) of float maps
  * (old/cluster_dino.py:345), writing int32 in that case is avoided: labels are uint8.      */

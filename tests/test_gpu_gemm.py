@@ -70,9 +70,34 @@ def test_gemm_kfeat_drops_cls():
     assert (out.float() - ref).abs().max().item() < 5e-3 * max(1.0, ref.abs().max().item())
 
 
+def test_gemm_vitb_shapes():
+    """The GEMM shapes of the metric's backbone (ViT-B/8, two 4097-token images): fc2 (K = 3072), the QKV split at
+    N = 2304 and fc1 + GELU at N = 3072."""
+    from vittf_b200 import _lib, ops
+    M, D, tokens = 2 * 4097, 768, 4097
+    a, w, b = _mk(M, D, 4 * D, seed=11)                                            # fc2: (8194, 768, 3072)
+    x = torch.randn(M, D, device="cuda")
+    want = x + _ref(a, w, b)
+    ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_RESID_F32, out=x)
+    assert (x - want).abs().max().item() < 4e-3 * max(1.0, want.abs().max().item())
+    a, w, b = _mk(M, 3 * D, D, seed=12)                                            # qkv: (8194, 2304, 768)
+    tok_pad = ops.tok_pad_of(tokens)
+    qk, vt = ops.gemm_bf16(a, w, b, _lib.EPI_QKV_SPLIT, tokens=tokens, tok_pad=tok_pad)
+    ref = _ref(a, w, b)
+    assert (qk.float() - ref[:, :2 * D]).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    v_ref = ref[:, 2 * D:].view(2, tokens, D).permute(0, 2, 1)
+    vt = vt.view(2, D, tok_pad)
+    assert (vt[:, :, :tokens].float() - v_ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert vt[:, :, tokens:].abs().max().item() == 0
+    a, w, b = _mk(M, 4 * D, D, seed=13)                                            # fc1 + GELU: (8194, 3072, 768)
+    g = ops.gemm_bf16(a, w, b, _lib.EPI_BIAS_GELU_BF16)
+    refg = torch.nn.functional.gelu(_ref(a, w, b))
+    assert (g.float() - refg).abs().max().item() < 2e-2 * max(1.0, refg.abs().max().item())
+
+
 @pytest.mark.parametrize("N", [384, 1152, 1536])
-def test_gemm_activation_resident_variant(N):
-    """M >= 148 row blocks and K <= 384 select the kernel that keeps the activation tile in shared memory."""
+def test_gemm_many_row_blocks(N):
+    """More row blocks than SMs (the persistent tile loop wraps) at K = 384, every epilogue."""
     from vittf_b200 import _lib, ops
     M, K = 148 * 128 + 77, 384
     a, w, b = _mk(M, N, K, seed=7)

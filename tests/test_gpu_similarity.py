@@ -85,7 +85,9 @@ def test_compute_similarities_with_bilateral_solver(golden):
                                                # fused tensor-core pass 1 (F % 32 == 0, d % 8 == 0) at awkward extents: odd h,
                                                # d below / not a multiple of the 64-voxel z tile, more than 32 prototypes
                                                ((5, 7, 16), (20, 28, 64), 32, 9), ((6, 5, 24), (24, 20, 96), 64, 40),
-                                               ((3, 3, 72), (12, 12, 288), 32, 5), ((9, 6, 8), (72, 48, 64), 96, 33)])
+                                               ((3, 3, 72), (12, 12, 288), 32, 5), ((9, 6, 8), (72, 48, 64), 96, 33),
+                                               # factor 2 on a 32-aligned grid (the configs[0] path) and a non-cubic factor-2 grid
+                                               ((32, 32, 32), (64, 64, 64), 32, 6), ((10, 6, 8), (20, 12, 16), 32, 11)])
 def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
     from oracle import similarity as osim, synth
     from vittf_b200.similarity import similarity_maps
@@ -119,9 +121,9 @@ def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
     assert torch.equal(lab[margin > 1e-2], ref_lab[margin > 1e-2])
 
 
-@pytest.mark.parametrize("F_,n,N,A,C", [(384, 64, 256, 32, 8), (768, 64, 512, 64, 16), (384, 128, 512, 24, 8)])
+@pytest.mark.parametrize("F_,n,N,A,C", [(384, 64, 128, 32, 4), (384, 64, 256, 32, 8), (768, 64, 512, 64, 16), (384, 128, 512, 24, 8)])
 def test_ns_similarity_full_size(F_, n, N, A, C):
-    """BASELINE.json shapes (configs[1], [2], [3]): spot check of 4096 random + all-corner output voxels against the point
+    """BASELINE.json shapes (configs[0] -- the factor-2 grid 64^3 -> 128^3 --, configs[1], [2], [3]): spot check of 4096 random + all-corner output voxels against the point
     oracle (2e-3), and the size-independent properties of the stage -- z-slab sharding invariance (bit-exact), invariance
     to the order of a class's prototypes (bit-exact), invariance to a power-of-two scale of the features (the NS
     composition normalises; bit-exact because every product scales exactly), values in [0, 1]."""
@@ -199,3 +201,31 @@ def test_compose_labels_matches_oracle():
     sims = (torch.rand(5, 20, 18, 16, generator=g) * 255).to(torch.uint8)
     thr = [0.486, 0.264, 0.236, 0.68, 0.291]                   # predict_ntf.py:208
     assert torch.equal(compose_labels(sims, thr), osim.compose_labels(sims, thr))
+
+
+@pytest.mark.parametrize("shape,z_range", [((24, 20, 16), None), ((21, 17, 13), None), ((32, 32, 32), (8, 20))])
+def test_quantized_maps_match_the_reference_expression(shape, z_range):
+    """predict_ntf.py:95-100 verbatim in torch -- quant = 0.99 * max, (255 / quant * sim).cpu().to(uint8) with its wrap above
+    255, F.interpolate(nearest) to half the grid -- against vittf_quantize_maps_u8, whole volumes
+    (even and odd extents) and a z-slab (the multi-GPU unit: global maxima, local planes).  Bit-exact."""
+    from vittf_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    C = 3
+    sims = torch.rand((C,) + shape, generator=g) ** 2
+    half = tuple(d // 2 for d in shape)
+    ref = []
+    for c in range(C):
+        quant = 0.99 * sims[c].max()
+        q = (255.0 / quant * sims[c]).to(torch.uint8)
+        ref.append(F.interpolate(q[None, None], half, mode="nearest")[0, 0])
+    ref = torch.stack(ref)
+    assert (ref < 3).any() and (ref == 255).any()                                  # the wrap and the top bin are exercised
+    sc = sims.cuda()
+    cmax = ops.class_max(sc)
+    if z_range is None:
+        out, zo = ops.quantize_maps_u8(sc, cmax, half)
+        assert zo == (0, half[2]) and torch.equal(out.cpu(), ref)
+    else:
+        z0, z1 = z_range
+        out, (zo0, zo1) = ops.quantize_maps_u8(sc[..., z0:z1].contiguous(), cmax, half, depth=shape[2], z0=z0)
+        assert (zo0, zo1) == (z0 // 2, z1 // 2) and torch.equal(out.cpu(), ref[..., zo0:zo1])

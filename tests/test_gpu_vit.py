@@ -34,7 +34,9 @@ def test_layernorm(D):
 
 @pytest.mark.parametrize("axis", ["z", "y", "x"])
 @pytest.mark.parametrize("shape,n_out", [((8, 4, 6), 4), ((7, 4, 6), 3), ((6, 4, 6), 6), ((20, 5, 7), 8), ((64, 9, 5), 16),
-                                         ((37, 4, 9), 24)])
+                                         ((37, 4, 9), 24),
+                                         # more pooled slabs than slices: AdaptiveAvgPool3d replicates slices
+                                         ((4, 4, 6), 8), ((5, 3, 4), 16), ((7, 4, 4), 24)])
 def test_pool_axis_matches_adaptive_avg_pool(axis, shape, n_out):
     from vittf_b200 import ops
     S, f0, f1 = shape
@@ -135,6 +137,54 @@ def test_vit_full_depth_512(golden):
     imgs = F.interpolate(fv.slice_images(vol, "z"), size=(512, 512), mode="nearest")
     torch.set_num_threads(max(1, torch.get_num_threads()))
     ref = fv.hooked_qkv(model, imgs)[:, 1:, 384:768].float()                      # (2, 4096, 384)
+    eng = engine_for(model, torch.device("cuda", 0), max_batch=2)
+    v = vol.cuda()
+    out = eng.k_features(v, "z", 0, 2, 512, 512, ops.minmax(v)).float().cpu()
+    cos = F.cosine_similarity(out, ref, dim=-1)
+    assert cos.min().item() >= 0.995, cos.min().item()
+    assert (out - ref).abs().max().item() < 0.05 * ref.abs().max().item()
+
+
+def test_feature_volume_smaller_than_feature_output_size():
+    """--slice-along all on a volume whose median extent is below --feature-output-size (32^3 with the default 64):
+    the reference pools S = 32 slices to 64 slabs (AdaptiveAvgPool3d replicates); same result here (bit-exact pooling of
+    the same K features, cosine vs the fp32 oracle)."""
+    from oracle import dino_vit, feature_volume as ofv, synth
+    from vittf_b200 import infer
+    vol, _ = synth.ct_volume((32, 32, 32), n_shells=4, seed=3)
+    model = dino_vit.build("vits8", seed=0, depth=2)
+    ref = ofv.feature_volume(vol, model, patch=8, fos=64, batch_size=8)
+    out = infer.feature_volume(vol, model, 8, 64, batch_size=8).cpu()
+    assert out.shape == ref.shape == (384, 64, 64, 64)
+    assert _cos_min(out, ref) >= 0.995
+
+
+def test_minmax_and_norm_minmax_accept_offset_views():
+    """A contiguous view with a storage offset (vol[1:]) is not 16-byte aligned; fp16 input keeps its dtype (infer.py:32-34)."""
+    from vittf_b200 import infer, ops
+    g = torch.Generator().manual_seed(0)
+    for dt in (torch.uint8, torch.float16, torch.float32):
+        v = (torch.rand(5, 7, 9, generator=g) * 200).to(dt).cuda()
+        view = v.flatten()[1:]
+        mm = ops.minmax(view)
+        assert mm[0].item() == view.float().min().item() and mm[1].item() == view.float().max().item()
+        n = infer.norm_minmax(view)
+        assert n.dtype == (torch.float16 if dt == torch.float16 else torch.float32)
+        ref = (view.float() - view.float().min()) / (view.float().max() - view.float().min())
+        assert (n.float() - ref).abs().max().item() < (1e-3 if dt == torch.float16 else 1e-6)
+
+
+def test_vitb8_full_depth_512():
+    """The metric's own backbone (BASELINE.json configs[2]; reference call site infer.py:176-177 with --dino-model vitb8,
+    infer.py:303): ViT-B/8, all 12 blocks, 512^2 input (4097 tokens), two slices vs the fp32 oracle.  Tolerance from
+    north_star: cosine >= 0.995 per patch."""
+    from oracle import dino_vit, feature_volume as fv, synth
+    from vittf_b200 import ops
+    from vittf_b200.vit import engine_for
+    model = dino_vit.build("vitb8", seed=0)
+    vol, _ = synth.ct_volume((512, 512, 2), n_shells=16, seed=1)                  # native 512^2 slices: resize factor 1, as at cfg3
+    imgs = fv.slice_images(vol, "z")
+    ref = fv.hooked_qkv(model, imgs)[:, 1:, 768:1536].float()                     # (2, 4096, 768)
     eng = engine_for(model, torch.device("cuda", 0), max_batch=2)
     v = vol.cuda()
     out = eng.k_features(v, "z", 0, 2, 512, 512, ops.minmax(v)).float().cpu()

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "vittf_sim_lowres": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     "vittf_sim_upsample": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p]),
     "vittf_class_max": (_i, [_p, _i, _i64, _p, _p]),
+    "vittf_quantize_maps_u8": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "vittf_labels": (_i, [_p, _i, _i, _i64, _p, _i, _p, _p]),
     "vittf_bls_workspace_bytes": (_i64, [C.POINTER(BlsParams), _i]),
     "vittf_bls_solve": (_i, [C.POINTER(BlsParams), _p, _p, _p, _p, _i, _p, _p, _p, _i64, _p]),

@@ -606,11 +606,11 @@ int attention_launch(const void* qk, const void* vt, void* out, int B, int token
         uint32_t box[2] = {64, HD};
         VITTF_CHECK(vittf_make_tmap(&tm_vt, vt, 2, 2, dims, strides, box, true));
     }
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceMemo configured;
+    if (!configured.cur()) {
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-        configured = true;
+        configured.cur() = 1;
     }
     const int units = ceil_div(tokens, 2 * BQ);
     AttnParams p{static_cast<__nv_bfloat16*>(out), tokens, heads, D, scale, flags, units * heads * B, units};

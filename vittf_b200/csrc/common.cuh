@@ -42,6 +42,16 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 int vittf_num_sms();
+// cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) is a PER-DEVICE setting: memoise it per device ordinal so a
+// second GPU used by the same process is configured too.
+struct PerDeviceMemo {
+    size_t v[64] = {};
+    size_t& cur() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return v[dev & 63];
+    }
+};
 void vittf_count_launches(int n);
 
 // 2-D .. 4-D tiled tensor maps (bf16/fp16 elements), built through the driver entry point so

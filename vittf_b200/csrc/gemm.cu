@@ -360,10 +360,10 @@ int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t 
         VITTF_CHECK(vittf_make_tmap(&tm_out, p.out, 2, 2, dims, strides, box, true));
     }
     auto kern = gemm_bf16_kernel<BN, EPI>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceMemo configured;
+    if (!configured.cur()) {
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
+        configured.cur() = 1;
     }
     const int tiles = ceil_div(p.M, BM) * (p.N / BN);
     const int grid = tiles < vittf_num_sms() ? tiles : vittf_num_sms();

@@ -452,10 +452,10 @@ int launch_lowres_tma_one(const CUtensorMap& tm, int F, int w, int h, int d, con
     const size_t stage = GRAM ? LF_STAGE_BYTES : LF_FS * LF_BX * LF_BY * LF_BZ * 2;
     const size_t smem = static_cast<size_t>(lf_stages<GRAM>()) * stage + static_cast<size_t>(F) * AT * 4 + 64;
     auto kern = sim_lowres_tma_kernel<AT, GRAM>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static PerDeviceMemo configured;
+    if (smem > configured.cur()) {
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
+        configured.cur() = smem;
     }
     dim3 grid(ceil_div(d, LF_BZ), ceil_div(h, LF_BY), ceil_div(w, LF_BX));
     kern<<<grid, 128, smem, s>>>(tm, F, w, h, d, protos, A, a_base, dots, gram);
@@ -584,10 +584,10 @@ int launch_dots_mma_one(const CUtensorMap& tm, int F, int64_t n, const float* pr
                         cudaStream_t s) {
     const size_t smem = static_cast<size_t>(DM_STAGES) * DM_STAGE_BYTES + static_cast<size_t>(8 * NT) * (F + 8) * 2 + 64 + 1024;
     auto kern = sim_dots_mma_kernel<NT>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static PerDeviceMemo configured;
+    if (smem > configured.cur()) {
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
+        configured.cur() = smem;
     }
     kern<<<static_cast<unsigned>(ceil_div_ll(n, DM_BM)), 128, smem, s>>>(tm, F, n, protos, A, a_base, dots);
     vittf_count_launches(1);
@@ -833,10 +833,10 @@ int launch_lowres_mma_one(const CUtensorMap& tm3, const CUtensorMap& tm1, int F,
     if (nstages < 3) return -1;
     const size_t smem = static_cast<size_t>(nstages) * GM_STAGE + panel + 2 * nstages * 8 + 128;
     auto kern = sim_lowres_mma_kernel<NT>;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static PerDeviceMemo configured;
+    if (smem > configured.cur()) {
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = smem;
+        configured.cur() = smem;
     }
     const int grid = ntiles < vittf_num_sms() ? ntiles : vittf_num_sms();
     kern<<<grid, 32 * (GM_CONSUMERS + 1), smem, s>>>(tm3, tm1, F, w, h, d, protos, A, dots, gram, tiles_y, tiles_z, ntiles, nstages);
@@ -1829,10 +1829,10 @@ int launch_rows(const UpParams& q, cudaStream_t s) {
     while (ac > 1 && bytes(ac) > 96 * 1024) ac /= 2;
     if (bytes(ac) > 200 * 1024) return -1;
     auto kern = sim_upsample_rows_kernel<U>;
-    static size_t configured = 0;
-    if (bytes(ac) > configured) {
+    static PerDeviceMemo configured;
+    if (bytes(ac) > configured.cur()) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes(ac))) != cudaSuccess) return -1;
-        configured = bytes(ac);
+        configured.cur() = bytes(ac);
     }
     dim3 grid(N, ceil_div(n + 1, cyb), U / rb);
     kern<<<grid, 256, bytes(ac), s>>>(q, cyb, rb, ac, i0, ng, czA, WZ);
@@ -1854,6 +1854,30 @@ __global__ void __launch_bounds__(256) class_max_kernel(const float* __restrict_
     if ((threadIdx.x & 31) == 0) {
         if (m >= 0.0f) atomicMax(reinterpret_cast<int*>(out + blockIdx.y), __float_as_int(m));
         else atomicMin(reinterpret_cast<unsigned int*>(out + blockIdx.y), __float_as_uint(m));
+    }
+}
+
+
+// predict_ntf.py:95-100: (255 / (0.99 * max_c) * sim).to(uint8) -- the C-style float -> int -> uint8 conversion of the
+// reference's CPU cast, values in (255, 257.6] wrap -- followed by F.interpolate(mode='nearest'):
+// src = min(floor(dst * in/out), in - 1).  The two commute, so only the kept voxels are read.
+__global__ void __launch_bounds__(256) quantize_maps_kernel(const float* __restrict__ sims, int W, int H, int zs, int z0, int D,
+                                                            const float* __restrict__ class_max, int Wo, int Ho, int Do,
+                                                            int zo0, int zos, uint8_t* __restrict__ out) {
+    const int c = blockIdx.y;
+    const float scale = 255.0f / (0.99f * class_max[c]);
+    const float sx = static_cast<float>(W) / Wo, sy = static_cast<float>(H) / Ho, sz = static_cast<float>(D) / Do;
+    const int64_t n_out = static_cast<int64_t>(Wo) * Ho * zos;
+    const float* src = sims + static_cast<int64_t>(c) * W * H * zs;
+    uint8_t* dst = out + static_cast<int64_t>(c) * n_out;
+    for (int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; o < n_out;
+         o += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int oz = static_cast<int>(o % zos) + zo0, oy = static_cast<int>((o / zos) % Ho),
+                  ox = static_cast<int>(o / (static_cast<int64_t>(zos) * Ho));
+        const int ix = min(static_cast<int>(floorf(ox * sx)), W - 1), iy = min(static_cast<int>(floorf(oy * sy)), H - 1),
+                  iz = min(static_cast<int>(floorf(oz * sz)), D - 1) - z0;
+        const float v = scale * __ldg(src + (static_cast<int64_t>(ix) * H + iy) * zs + iz);
+        dst[o] = static_cast<uint8_t>(static_cast<int>(v));
     }
 }
 
@@ -2048,6 +2072,31 @@ extern "C" int vittf_class_max(const float* sims, int C, int64_t n, float* out, 
     class_max_kernel<<<grid, 256, 0, s>>>(sims, n, out);
     VITTF_CHECK_CUDA(cudaGetLastError());
     vittf_count_launches(2);
+    return VITTF_OK;
+}
+
+extern "C" int vittf_quantize_maps_u8(const float* sims, int C, int W, int H, int D, int z0, int z1, const float* class_max,
+                                      int Wo, int Ho, int Do, int zo0, int zo1, uint8_t* out, void* stream) {
+    VITTF_REQUIRE(sims && class_max && out, "vittf_quantize_maps_u8: null pointer");
+    VITTF_REQUIRE(C > 0 && C <= 65535 && W > 0 && H > 0 && D > 0 && z0 >= 0 && z1 > z0 && z1 <= D && Wo > 0 && Ho > 0 && Do > 0 &&
+                      zo0 >= 0 && zo1 >= zo0 && zo1 <= Do,
+                  "vittf_quantize_maps_u8: bad sizes (C=%d in=%dx%dx%d z=[%d,%d) out=%dx%dx%d zo=[%d,%d))", C, W, H, D, z0, z1, Wo,
+                  Ho, Do, zo0, zo1);
+    if (zo1 == zo0) return VITTF_OK;
+    // every requested output plane must read a source plane of the slab
+    const float sz = static_cast<float>(D) / Do;
+    auto src_plane = [&](int oz) { const int i = static_cast<int>(floorf(oz * sz)); return i < D - 1 ? i : D - 1; };
+    VITTF_REQUIRE(src_plane(zo0) >= z0 && src_plane(zo1 - 1) < z1, "vittf_quantize_maps_u8: output planes [%d,%d) read outside the slab [%d,%d)",
+                  zo0, zo1, z0, z1);
+    const int64_t n_out = static_cast<int64_t>(Wo) * Ho * (zo1 - zo0);
+    int64_t blocks = ceil_div_ll(n_out, 256);
+    const int64_t cap = static_cast<int64_t>(vittf_num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    dim3 grid(static_cast<unsigned>(blocks), C);
+    quantize_maps_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(sims, W, H, z1 - z0, z0, D, class_max, Wo, Ho, Do, zo0,
+                                                                              zo1 - zo0, out);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
     return VITTF_OK;
 }
 

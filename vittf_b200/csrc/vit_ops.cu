@@ -655,11 +655,11 @@ extern "C" int vittf_patch_embed(const void* vol, int vol_dtype, int X, int Y, i
         dim3 grid_m(n_items < vittf_num_sms() ? n_items : vittf_num_sms(), D / PE_DCH);
 #define LAUNCH_PEM(T)                                                                                                   \
     do {                                                                                                                \
-        static bool configured = false;                                                                                 \
-        if (!configured) {                                                                                              \
+        static PerDeviceMemo configured;                                                                                 \
+        if (!configured.cur()) {                                                                                              \
             VITTF_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                   static_cast<int>(smem_m)));                                          \
-            configured = true;                                                                                          \
+            configured.cur() = 1;                                                                                          \
         }                                                                                                               \
         patch_embed_mma_kernel<T><<<grid_m, PM_THREADS, smem_m, s>>>(q, n_imgs);                                               \
     } while (0)
@@ -680,11 +680,11 @@ extern "C" int vittf_patch_embed(const void* vol, int vol_dtype, int X, int Y, i
         dim3 grid_t(n_items < vittf_num_sms() ? n_items : vittf_num_sms(), D / PE_DCH);
 #define LAUNCH_PET(T)                                                                                                   \
     do {                                                                                                                \
-        static bool configured = false;                                                                                 \
-        if (!configured) {                                                                                              \
+        static PerDeviceMemo configured;                                                                                 \
+        if (!configured.cur()) {                                                                                              \
             VITTF_CHECK_CUDA(cudaFuncSetAttribute(patch_embed_tiled_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                   static_cast<int>(smem_t)));                                          \
-            configured = true;                                                                                          \
+            configured.cur() = 1;                                                                                          \
         }                                                                                                               \
         patch_embed_tiled_kernel<T><<<grid_t, 256, smem_t, s>>>(q, n_items);                                            \
     } while (0)
@@ -746,7 +746,8 @@ extern "C" int vittf_layernorm(const float* x, const float* w, const float* b, v
 extern "C" int vittf_pool_axis(const void* k_f16, int S, int slice0, int n_local, int f0, int f1, int D, int axis,
                                int n_out, int o0, int o1, void* out_f16, int accumulate, void* stream) {
     VITTF_REQUIRE(k_f16 && out_f16, "vittf_pool_axis: null pointer");
-    VITTF_REQUIRE(S > 0 && f0 > 0 && f1 > 0 && D > 0 && n_out > 0 && n_out <= S, "vittf_pool_axis: bad sizes");
+    // n_out > S is legal (AdaptiveAvgPool3d replicates slices: every window [floor(o*S/n), ceil((o+1)*S/n)) is non-empty)
+    VITTF_REQUIRE(S > 0 && f0 > 0 && f1 > 0 && D > 0 && n_out > 0, "vittf_pool_axis: bad sizes");
     VITTF_REQUIRE(o0 >= 0 && o1 > o0 && o1 <= n_out, "vittf_pool_axis: slab range [%d,%d) outside [0,%d)", o0, o1, n_out);
     {
         const int need0 = static_cast<int>((static_cast<int64_t>(o0) * S) / n_out);

@@ -59,6 +59,24 @@ class DinoWeights(nn.Module):
                            "(vittf_b200.infer.compute_qkv)")
 
 
+def unwrap_checkpoint(sd):
+    """Accepts the backbone-only state dicts torch.hub serves as well as the official FULL DINO checkpoints
+    ({'teacher': ..., 'student': ...} with 'module.' / 'backbone.' prefixes and projection-head entries)."""
+    if isinstance(sd, dict):
+        for key in ("teacher", "state_dict", "model"):
+            if key in sd and isinstance(sd[key], dict):
+                sd = sd[key]
+                break
+    out = {}
+    for k, v in sd.items():
+        for pre in ("module.", "backbone."):
+            if k.startswith(pre):
+                k = k[len(pre):]
+        if not k.startswith("head."):
+            out[k] = v
+    return out
+
+
 def build_dino(name, weights=None, seed=0):
     """DINO-style random init under `seed` (trunc-normal 0.02 for Linear / pos / cls, LayerNorm 1/0,
     Conv2d default), or the parameters of a DINO checkpoint."""
@@ -77,7 +95,7 @@ def build_dino(name, weights=None, seed=0):
     torch.random.set_rng_state(gen_state)
     if weights is not None:
         sd = torch.load(weights, map_location="cpu", weights_only=False)
-        sd = sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+        sd = unwrap_checkpoint(sd)
         missing, unexpected = m.load_state_dict(sd, strict=False)
         if missing:
             raise RuntimeError(f"checkpoint {weights} lacks parameters: {missing[:5]}...")

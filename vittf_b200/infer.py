@@ -45,7 +45,8 @@ def norm_minmax(t):
     """(t - min) / (max - min) (infer.py:32-34); the range comes from the native reduction for CUDA input."""
     if t.is_cuda and t.dtype in (torch.uint8, torch.float16, torch.float32) and t.is_contiguous():
         mm = ops.minmax(t)
-        return (t.float() - mm[0]) / (mm[1] - mm[0])
+        out = (t.float() - mm[0]) / (mm[1] - mm[0])
+        return out.to(t.dtype) if t.dtype == torch.float16 else out      # the reference keeps a floating input dtype
     mi, ma = t.min(), t.max()
     return (t - mi) / (ma - mi)
 

@@ -13,6 +13,23 @@ from ._lib import DTYPE_CODE, check, load, ptr, require_cuda, stream_ptr
 AXIS_INDEX = {"x": 0, "y": 1, "z": 2}
 
 
+def _on_device(fn):
+    """Runs the wrapped entry point with the CUDA device of its first CUDA tensor argument current: kernels launch on
+    the current device, so a tensor on another GPU (e.g. compute_qkv(dev='cuda:1')) must switch to it first."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def tok_pad_of(tokens):
     return (tokens + 127) // 128 * 128
 
@@ -23,13 +40,17 @@ def device_arch():
     return out.value
 
 
+@_on_device
 def minmax(vol):
     require_cuda(vol)
+    if vol.data_ptr() % 16:                 # a contiguous view with a storage offset (vol[1:]): the kernel reads 16-byte words
+        vol = vol.clone()
     out = torch.empty(2, dtype=torch.float32, device=vol.device)
     check(load().vittf_minmax(ptr(vol), vol.numel(), DTYPE_CODE[vol.dtype], ptr(out), stream_ptr(vol.device)), "vittf_minmax")
     return out
 
 
+@_on_device
 def gemm_bf16(a, w, bias, epi, out=None, out2=None, tokens=0, tok_pad=0):
     """a (M,K) bf16, w (N,K) bf16, bias (N) fp32; see include/vittf.h for the epilogues."""
     require_cuda(a, w, bias, out, out2)
@@ -51,6 +72,7 @@ def gemm_bf16(a, w, bias, epi, out=None, out2=None, tokens=0, tok_pad=0):
     return (out, out2) if epi == _lib.EPI_QKV_SPLIT else out
 
 
+@_on_device
 def attention(qk, vt, batch, tokens, heads, tok_pad):
     require_cuda(qk, vt)
     out = torch.empty(batch * tokens, heads * 64, dtype=torch.bfloat16, device=qk.device)
@@ -59,6 +81,7 @@ def attention(qk, vt, batch, tokens, heads, tok_pad):
     return out
 
 
+@_on_device
 def attention_prescaled(qk, vt, batch, tokens, heads, tok_pad, return_flags=False):
     """softmax(q k^T) v for q already multiplied by hd^-0.5 * log2(e): max-free first pass + safe pass over flagged CTAs."""
     require_cuda(qk, vt)
@@ -70,6 +93,7 @@ def attention_prescaled(qk, vt, batch, tokens, heads, tok_pad, return_flags=Fals
     return (out, ws) if return_flags else out
 
 
+@_on_device
 def layernorm(x, w, b):
     require_cuda(x, w, b)
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
@@ -78,6 +102,7 @@ def layernorm(x, w, b):
     return y
 
 
+@_on_device
 def patch_embed(vol, axis, s0, s1, im0, im1, patch, mm, patch_w, patch_b, pos):
     require_cuda(vol, mm, patch_w, patch_b, pos)
     D = patch_b.numel()
@@ -90,6 +115,7 @@ def patch_embed(vol, axis, s0, s1, im0, im1, patch, mm, patch_w, patch_b, pos):
     return out
 
 
+@_on_device
 def pool_axis(k, f0, f1, axis, n_out, out=None, accumulate=False, total_slices=None, slice0=0, slabs=None):
     """k (S, f0*f1, D) fp16 -> (D, ., ., .) fp16 in the reference layout (infer.py:203).
     Sharded use: k holds global slices [slice0, slice0+S) of `total_slices`; only output slabs
@@ -109,6 +135,7 @@ def pool_axis(k, f0, f1, axis, n_out, out=None, accumulate=False, total_slices=N
     return out
 
 
+@_on_device
 def accumulate_f16(out, inp):
     """out = fp16(out + inp) in place (infer.py:332)."""
     require_cuda(out, inp)
@@ -117,6 +144,7 @@ def accumulate_f16(out, inp):
     return out
 
 
+@_on_device
 def sample_prototypes(feats, rel, mode):
     require_cuda(feats, rel)
     F, w, h, d = feats.shape
@@ -128,6 +156,7 @@ def sample_prototypes(feats, rel, mode):
     return out
 
 
+@_on_device
 def sim_lowres(feats, protos, want_gram=True):
     require_cuda(feats, protos)
     F, w, h, d = feats.shape
@@ -140,6 +169,7 @@ def sim_lowres(feats, protos, want_gram=True):
     return dots, gram
 
 
+@_on_device
 def sim_upsample(dots, gram, lr_shape, class_offsets, out_shape, mode, threshold=0.25, exponent=2.0, z0=0, z1=None, out=None):
     require_cuda(dots, gram, class_offsets, out)
     w, h, d = lr_shape
@@ -154,6 +184,7 @@ def sim_upsample(dots, gram, lr_shape, class_offsets, out_shape, mode, threshold
     return out
 
 
+@_on_device
 def class_max(sims):
     require_cuda(sims)
     C_ = sims.shape[0]
@@ -162,6 +193,30 @@ def class_max(sims):
     return out
 
 
+def nearest_src(o, n_in, n_out):
+    """Source index of F.interpolate(mode='nearest'): min(floor(o * in/out), in - 1) in fp32 like ATen."""
+    import numpy as np
+    return min(int(np.floor(np.float32(o) * (np.float32(n_in) / np.float32(n_out)))), n_in - 1)
+
+
+@_on_device
+def quantize_maps_u8(sims, cmax, out_shape, depth=None, z0=0):
+    """predict_ntf.py:95-100: sims fp32 (C, W, H, zs) = z-slab [z0, z0+zs) of a (W, H, depth) grid, cmax fp32 (C) the
+    GLOBAL per-class maxima -> (uint8 (C, Wo, Ho, zo1-zo0), (zo0, zo1)): the wrapped uint8 quantisation, nearest-resized
+    to out_shape = (Wo, Ho, Do); [zo0, zo1) are the output planes whose source plane lies in the slab."""
+    require_cuda(sims, cmax)
+    C_, W, H, zs = sims.shape
+    D = zs if depth is None else depth
+    Wo, Ho, Do = out_shape
+    planes = [o for o in range(Do) if z0 <= nearest_src(o, D, Do) < z0 + zs]
+    zo0, zo1 = (planes[0], planes[-1] + 1) if planes else (0, 0)
+    out = torch.empty(C_, Wo, Ho, zo1 - zo0, dtype=torch.uint8, device=sims.device)
+    check(load().vittf_quantize_maps_u8(ptr(sims), C_, W, H, D, z0, z0 + zs, ptr(cmax), Wo, Ho, Do, zo0, zo1, ptr(out),
+                                        stream_ptr(sims.device)), "vittf_quantize_maps_u8")
+    return out, (zo0, zo1)
+
+
+@_on_device
 def labels(sims, thresholds_u8=None, mode=0):
     require_cuda(sims, thresholds_u8)
     C_ = sims.shape[0]
@@ -171,6 +226,7 @@ def labels(sims, thresholds_u8=None, mode=0):
     return out
 
 
+@_on_device
 def sobel_confidence(r_u8):
     require_cuda(r_u8)
     W, H, D = r_u8.shape
@@ -181,6 +237,7 @@ def sobel_confidence(r_u8):
     return out
 
 
+@_on_device
 def bls_solve(t, r_u8, conf, luma_lut, sigma_spatial, lam, diag_min, cg_tol, cg_maxiter, luma_bins):
     """t (nrhs,W,H,D) fp32, r_u8 (W,H,D) uint8, conf (W,H,D) fp32 or None -> (out fp32 (nrhs,W,H,D), iters int32)."""
     require_cuda(t, r_u8, conf, luma_lut)
@@ -198,6 +255,7 @@ def bls_solve(t, r_u8, conf, luma_lut, sigma_spatial, lam, diag_min, cg_tol, cg_
     return out, iters
 
 
+@_on_device
 def bls_solve_sharded(t_slab, r_u8, conf_slab, luma_lut, sigma_spatial, lam, diag_min, cg_tol, cg_maxiter, luma_bins, z0, z1,
                       all_reduce_max=None, all_reduce_sum=None):
     """The solver in stages over the z-slab [z0, z1) of this rank: t_slab (nrhs,W,H,z1-z0) fp32,
@@ -242,6 +300,7 @@ def bls_solve_sharded(t_slab, r_u8, conf_slab, luma_lut, sigma_spatial, lam, dia
     return out, iters
 
 
+@_on_device
 def binary_erosion(mask_u8, connectivity):
     """scipy.ndimage.binary_erosion(mask, generate_binary_structure(3, connectivity)) (border_value 0) on the device:
     mask uint8 (W,H,D) -> uint8 (W,H,D)."""
@@ -255,6 +314,7 @@ def binary_erosion(mask_u8, connectivity):
     return out
 
 
+@_on_device
 def topk_voxels(maps, K):
     """maps fp32 (n_maps, n) CUDA -> (int64 (n_maps, K) flat indices, fp32 (n_maps) thresholds) with the tie rule of
     infer.py:92-93 (first K voxels in index order with value >= K-th largest value)."""
@@ -266,6 +326,7 @@ def topk_voxels(maps, K):
     return idx, thr
 
 
+@_on_device
 def mean_pairwise_distance(feats, measure):
     """feats fp32 (N, F) CUDA -> fp32 (N): 1 - mean cosine similarity ('cosine') or mean Euclidean distance ('euclidean')."""
     require_cuda(feats)
@@ -279,6 +340,7 @@ def mean_pairwise_distance(feats, measure):
     return out
 
 
+@_on_device
 def confusion_matrix(truth_u8, pred_u8, K):
     """(K, K) int64 table of (true, predicted) label pairs of two uint8 CUDA tensors of equal size (rows = true labels,
     as sklearn.metrics.confusion_matrix); labels >= K raise."""

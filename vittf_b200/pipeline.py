@@ -35,6 +35,19 @@ def volume_to_similarity(vol_dev, model, annotations, patch=8, fos=64, batch_siz
     return feats, sims, labels, zr
 
 
+def quantized_maps(sims_slab, z_range, depth, group=None):
+    """The uint8 maps compute_similarities hands back (predict_ntf.py:95-100: 0.99*max quantisation with the
+    reference's wrap, nearest-resized to half the grid) for this rank's z-slab of fp32 maps (C,W,H,z1-z0).  The class
+    maxima are global: one all-reduce(max) of C floats when several ranks hold slabs.
+    Returns (uint8 (C, W//2, H//2, planes of this slab), (zo0, zo1))."""
+    import torch.distributed as td
+    cmax = ops.class_max(sims_slab)
+    if td.is_available() and td.is_initialized() and td.get_world_size(group) > 1:
+        td.all_reduce(cmax, op=td.ReduceOp.MAX, group=group)
+    C_, W, H, _ = sims_slab.shape
+    return ops.quantize_maps_u8(sims_slab, cmax, (W // 2, H // 2, depth // 2), depth=depth, z0=z_range[0])
+
+
 def refine_similarity(sims_slab, ref_u8, z_range, grid_params=None, bs_params=None, group=None):
     """bilateral_solver3d refinement of per-class maps (configs[4]): sims_slab fp32 (C,W,H,z1-z0) = this rank's
     z-slab, ref_u8 the full grey uint8 volume (W,H,D) at the maps' resolution.  All classes share the reference and

@@ -147,9 +147,10 @@ class VitEngine:
             out = torch.empty(B, f0 * f1, self.embed_dim, dtype=torch.float16, device=self.device)
         ws = self._workspace(B, tokens)
         X, Y, Z = vol.shape
-        check(load().vittf_vit_k_features(self._handle, ptr(vol), _lib.DTYPE_CODE[vol.dtype], X, Y, Z, AXIS_INDEX[axis],
-                                          s0, s1, im0, im1, ptr(mm), ptr(self.pos_for(im0, im1)), ptr(out), ptr(ws),
-                                          ws.numel(), stream_ptr(self.device)), "vittf_vit_k_features")
+        with torch.cuda.device(self.device):          # the engine's device need not be the current one
+            check(load().vittf_vit_k_features(self._handle, ptr(vol), _lib.DTYPE_CODE[vol.dtype], X, Y, Z, AXIS_INDEX[axis],
+                                              s0, s1, im0, im1, ptr(mm), ptr(self.pos_for(im0, im1)), ptr(out), ptr(ws),
+                                              ws.numel(), stream_ptr(self.device)), "vittf_vit_k_features")
         return out
 
 
