@@ -156,9 +156,13 @@ int vittf_sample_prototypes(const void* feats, int feat_dtype, int F, int w, int
  *   dots  fp32 (A, n_lr)   <f_v, p_a>         (einsum 'fwhd,caf->cawhd', predict_ntf.py:65)
  *   gram  fp32 (14, n_lr)  <f_v, f_{v+o}> for o in {0} U 13 forward neighbours (may be
  *                             NULL): lets the up-sampling pass evaluate |interp(f)|^2
- *                             without materialising interp(f).         */
+ *                             without materialising interp(f).
+ *   dots_layout 0: dots fp32 (A, n_lr).  1: dots fp32 (n_lr, A4) with A4 = A rounded up to a multiple of 4 (voxel-major: the
+ *   tcgen05 up-sampling kernel gathers the corner dots of 4 prototypes with one 16-byte load); only the fused tensor-core pass
+ *   writes it -- vittf_sim_lowres_layout() tells whether it is available for an input (1) or not (0). */
+int vittf_sim_lowres_layout(int feat_dtype, int F, int w, int h, int d, const void* feats);
 int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w, int h, int d, const float* protos, int A,
-                     float* dots, float* gram, void* stream);
+                     float* dots, float* gram, int dots_layout, void* stream);
 
 typedef enum {
     VITTF_SIM_NS = 0,     /* interp(features) -> L2 normalise -> dot -> clamp(0,1)^e -> class MAX */
@@ -174,7 +178,7 @@ typedef enum {
  *   class_offsets int32 (C+1) prefix offsets into the A prototypes.                        */
 int vittf_sim_upsample(const float* dots, const float* gram, int w, int h, int d, int A, const int* class_offsets,
                        int C, int W, int H, int D, int z0, int z1, int mode, float threshold, float exponent,
-                       float* out, void* stream);
+                       int dots_layout, float* out, void* stream);
 
 /* 0.99*max quantisation input (predict_ntf.py:95): per-class maximum, out fp32 (C) */
 int vittf_class_max(const float* sims, int C, int64_t n, float* out, void* stream);

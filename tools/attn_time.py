@@ -2,7 +2,7 @@ import sys, torch
 sys.path.insert(0, '.')
 from vittf_b200 import ops
 import os
-B, tokens, heads = int(os.environ.get('B', 8)), 4097, 6
+B, tokens, heads = int(os.environ.get("B", 8)), 4097, int(os.environ.get("HEADS", 6))
 D = heads * 64
 qk = torch.randn(B * tokens, 2, D, device="cuda")
 PRE = os.environ.get("PRESCALED", "1") == "1"

@@ -73,7 +73,7 @@ def main():
         med1, _ = timeit(lambda: ops.sim_lowres(feats, protos), flush=flush)
         low = ops.sim_lowres(feats, protos)
         out = torch.empty(8, 256, 256, 256, device="cuda")
-        med2, _ = timeit(lambda: ops.sim_upsample(low[0], low[1], (64, 64, 64), offs, (256, 256, 256), 0, out=out), flush=flush)
+        med2, _ = timeit(lambda: ops.sim_upsample(low[0], low[1], (64, 64, 64), offs, (256, 256, 256), 0, out=out, layout=low[2]), flush=flush)
         bytes1 = feats.numel() * 2 + (A + 14) * 64 ** 3 * 4
         bytes2 = (A + 14) * 64 ** 3 * 4 + out.numel() * 4
         res[f"sim_A{A}"] = {"lowres_ms": med1, "lowres_gbs": bytes1 / med1 / 1e6, "upsample_ms": med2,

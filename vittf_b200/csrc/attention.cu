@@ -103,6 +103,42 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
     p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
     p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
+#ifndef POLY_GUARD_V
+#define POLY_GUARD_V 1     // max-free pass: 1 = one 3-input |x| maximum per polynomial pair feeds the range flag, 0 = clamp every input
+#endif
+#ifndef POLY_DEG_V
+#define POLY_DEG_V 3
+#endif
+// 2^x for the max-free pass: as above without the four per-pair clamps.  The exponent field only holds round(x) in
+// [-126, 127]; instead of clamping, the largest |x| that went through the polynomial is tracked (ONE 3-input maximum per
+// pair) and the work item is handed to the safe pass when it exceeds 126 -- exactly like the range check on the row sum.
+__device__ __forceinline__ void exp2_poly2_fast(float x0, float x1, float& p0, float& p1, float& track) {
+    const float magic = 12582912.0f;
+    if (POLY_GUARD_V == 1) {
+        asm("max.f32 %0, %0, %1, %2;" : "+f"(track) : "f"(fabsf(x0)), "f"(fabsf(x1)));
+    } else {
+        x0 = fmaxf(fminf(x0, 126.0f), -126.0f);
+        x1 = fmaxf(fminf(x1, 126.0f), -126.0f);
+    }
+    const ptx::F2 x = ptx::f2_make(x0, x1);
+    const ptx::F2 t = ptx::f2_add(x, ptx::f2_make(magic, magic));
+    const ptx::F2 n = ptx::f2_add(t, ptx::f2_make(-magic, -magic));
+    const ptx::F2 fr = ptx::f2_fma(n, ptx::f2_make(-1.0f, -1.0f), x);
+    ptx::F2 q;
+    if (POLY_DEG_V == 3) {
+        q = ptx::f2_fma(fr, ptx::f2_make(0.05508868f, 0.05508868f), ptx::f2_make(0.24260405f, 0.24260405f));
+        q = ptx::f2_fma(q, fr, ptx::f2_make(0.69327623f, 0.69327623f));
+        q = ptx::f2_fma(q, fr, ptx::f2_make(0.99992895f, 0.99992895f));
+    } else {                                               // relative error 1.7e-3: below the rounding of P to bf16 (2^-9)
+        q = ptx::f2_fma(fr, ptx::f2_make(0.2384257f, 0.2384257f), ptx::f2_make(0.7034428f, 0.7034428f));
+        q = ptx::f2_fma(q, fr, ptx::f2_make(1.000443f, 1.000443f));
+    }
+    float t0, t1, q0, q1;
+    ptx::f2_get(t, t0, t1);
+    ptx::f2_get(q, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 #ifndef POLY_EVERY_V
 #define POLY_EVERY_V 4     // measured on B200: 4 (25 %) > 0 > 2
 #endif
@@ -344,7 +380,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                 // maximum as long as the exponents stay inside what bf16 P and fp32 O / l can hold; rows that leave that
                 // range are detected on l afterwards and their item is redone by the safe kernel.  Per score: MUFU (or the
                 // FMA-pipe polynomial), half an FADD2 and half an F2FP -- no scale FMA, no max, no rescale logic.
-                float l_f = 0.0f;
+                float l_f = 0.0f, track = 0.0f;
                 for (int j = 0; j < nfull; ++j) {
                     if (q == 0 && lane == 0) TRACE(t, j, 0);
                     ptx::mbar_wait_quiet(&s_full[t], (gt + j) & 1);
@@ -368,7 +404,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                             const float x0 = __uint_as_float(s[ch][2 * i]), x1 = __uint_as_float(s[ch][2 * i + 1]);
                             float p0, p1;
                             if (poly_slot(ch * 16 + i)) {
-                                exp2_poly2(fminf(x0, 126.0f), fminf(x1, 126.0f), p0, p1);   // 2^126 still trips the range check
+                                exp2_poly2_fast(x0, x1, p0, p1, track);
                             } else {
                                 p0 = ptx::ex2_approx(x0);
                                 p1 = ptx::ex2_approx(x1);
@@ -419,7 +455,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
                 // 2^-100 < l < 2^100 bounds every p (and p * v) far away from fp32 overflow and from total underflow;
                 // anything else (inf, NaN, 0) sends the item to the safe pass.  Padding rows beyond `tokens` are ignored.
                 const bool row_live = (item % p.units) * 2 * BQ + t * BQ + q * 32 + lane < p.tokens;
-                if (row_live && !(l_f > 7.888609052210118e-31f && l_f < 1.2676506002282294e30f)) p.flags[item] = 1;
+                if (row_live && !(l_f > 7.888609052210118e-31f && l_f < 1.2676506002282294e30f && track <= 126.0f)) p.flags[item] = 1;
                 l = l_f;
             } else {
             const float c = p.scale_log2e;

@@ -13,5 +13,5 @@ for f in attention gemm similarity; do
 done
 wait
 "${NVCC}" -gencode arch=compute_100a,code=sm_100a -shared -o "${HERE}/../libvittf_b200_${NAME}.so" \
-  "${HERE}"/build/${NAME}/{attention,gemm,similarity}.o "${HERE}"/build/{api,vit_ops,vit_engine,bls,sampling}.o -lcudart
+  "${HERE}"/build/${NAME}/{attention,gemm,similarity}.o "${HERE}"/build/{api,vit_ops,vit_engine,sim_up_tc,bls,sampling}.o -lcudart
 echo "built libvittf_b200_${NAME}.so"

@@ -13,6 +13,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "sim_internal.h"
 
 namespace {
 
@@ -489,7 +490,7 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
 template <int NT>   // N-tiles of 8 prototypes handled by the CTA (A <= 8 * NT)
 __global__ void __launch_bounds__(128) sim_dots_mma_kernel(const __grid_constant__ CUtensorMap tm_f, int F, int64_t n,
                                                            const float* __restrict__ protos, int A, int a_base,
-                                                           float* __restrict__ dots) {
+                                                           float* __restrict__ dots, int64_t sa, int64_t sv) {
     extern __shared__ __align__(1024) uint8_t dm_smem_raw[];
     uint8_t* dm_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dm_smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_t = dm_smem;                                                   // [stage][box][32 f][64 v] halves, swizzled
@@ -575,13 +576,13 @@ __global__ void __launch_bounds__(128) sim_dots_mma_kernel(const __grid_constant
             for (int e = 0; e < 4; ++e) {
                 const int a = a_base + 8 * j + 2 * (lane & 3) + (e & 1);
                 const int64_t v = v0 + wid * 32 + m * 16 + (lane >> 2) + (e >> 1) * 8;
-                if (a < A && v < n) dots[static_cast<size_t>(a) * n + v] = acc[m][j][e];
+                if (a < A && v < n) dots[a * sa + v * sv] = acc[m][j][e];
             }
 }
 
 template <int NT>
 int launch_dots_mma_one(const CUtensorMap& tm, int F, int64_t n, const float* protos, int A, int a_base, float* dots,
-                        cudaStream_t s) {
+                        int64_t sa, int64_t sv, cudaStream_t s) {
     const size_t smem = static_cast<size_t>(DM_STAGES) * DM_STAGE_BYTES + static_cast<size_t>(8 * NT) * (F + 8) * 2 + 64 + 1024;
     auto kern = sim_dots_mma_kernel<NT>;
     static PerDeviceMemo configured;
@@ -589,13 +590,15 @@ int launch_dots_mma_one(const CUtensorMap& tm, int F, int64_t n, const float* pr
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured.cur() = smem;
     }
-    kern<<<static_cast<unsigned>(ceil_div_ll(n, DM_BM)), 128, smem, s>>>(tm, F, n, protos, A, a_base, dots);
+    kern<<<static_cast<unsigned>(ceil_div_ll(n, DM_BM)), 128, smem, s>>>(tm, F, n, protos, A, a_base, dots, sa, sv);
     vittf_count_launches(1);
     return VITTF_OK;
 }
 
 // all prototypes, 64 per launch
-int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, int A, float* dots, cudaStream_t s, int a_first = 0) {
+int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, int A, float* dots, cudaStream_t s, int a_first = 0,
+                    int64_t sa = -1, int64_t sv = 1) {
+    if (sa < 0) sa = n;
     CUtensorMap tm;
     const uint64_t dims[2] = {static_cast<uint64_t>(n), static_cast<uint64_t>(F)};
     const uint64_t strides[1] = {static_cast<uint64_t>(n) * 2};
@@ -604,10 +607,10 @@ int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, 
     for (int a_base = a_first; a_base < A; a_base += 64) {
         const int rem = A - a_base;
         int rc;
-        if (rem > 32) rc = launch_dots_mma_one<8>(tm, F, n, protos, A, a_base, dots, s);
-        else if (rem > 16) rc = launch_dots_mma_one<4>(tm, F, n, protos, A, a_base, dots, s);
-        else if (rem > 8) rc = launch_dots_mma_one<2>(tm, F, n, protos, A, a_base, dots, s);
-        else rc = launch_dots_mma_one<1>(tm, F, n, protos, A, a_base, dots, s);
+        if (rem > 32) rc = launch_dots_mma_one<8>(tm, F, n, protos, A, a_base, dots, sa, sv, s);
+        else if (rem > 16) rc = launch_dots_mma_one<4>(tm, F, n, protos, A, a_base, dots, sa, sv, s);
+        else if (rem > 8) rc = launch_dots_mma_one<2>(tm, F, n, protos, A, a_base, dots, sa, sv, s);
+        else rc = launch_dots_mma_one<1>(tm, F, n, protos, A, a_base, dots, sa, sv, s);
         VITTF_CHECK(rc);
     }
     VITTF_CHECK_CUDA(cudaGetLastError());
@@ -642,7 +645,7 @@ template <int NT>   // n-tiles of 8 prototypes (A <= 8 * NT)
 __global__ void __maxnreg__(168)
     sim_lowres_mma_kernel(const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm1, int F, int w, int h, int d,
                           const float* __restrict__ protos, int A, float* __restrict__ dots, float* __restrict__ gram,
-                          int tiles_y, int tiles_z, int ntiles, int nstages) {
+                          int tiles_y, int tiles_z, int ntiles, int nstages, int64_t sa, int64_t sv) {
     extern __shared__ __align__(1024) uint8_t gm_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gm_raw) + 127) & ~uintptr_t(127));
     uint8_t* s_t = smem;                                                                   // [stage][X | P | Q]
@@ -798,7 +801,7 @@ __global__ void __maxnreg__(168)
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int aa = 8 * j + 2 * t + (e & 1);
-                if (ok && aa < A) dots[static_cast<int64_t>(aa) * n + vb + row] = acc_d[j][e];
+                if (ok && aa < A) dots[aa * sa + (vb + row) * sv] = acc_d[j][e];
             }
             if (gram != nullptr) {
 #pragma unroll
@@ -824,7 +827,7 @@ __global__ void __maxnreg__(168)
 
 template <int NT>
 int launch_lowres_mma_one(const CUtensorMap& tm3, const CUtensorMap& tm1, int F, int w, int h, int d, const float* protos, int A,
-                          float* dots, float* gram, cudaStream_t s) {
+                          float* dots, float* gram, int64_t sa, int64_t sv, cudaStream_t s) {
     const int tiles_z = ceil_div(d, GM_TZ), tiles_y = ceil_div(h, 2);
     const int ntiles = tiles_z * tiles_y * w;
     const size_t panel = static_cast<size_t>(8 * NT) * (F + 8) * 2;
@@ -839,14 +842,18 @@ int launch_lowres_mma_one(const CUtensorMap& tm3, const CUtensorMap& tm1, int F,
         configured.cur() = smem;
     }
     const int grid = ntiles < vittf_num_sms() ? ntiles : vittf_num_sms();
-    kern<<<grid, 32 * (GM_CONSUMERS + 1), smem, s>>>(tm3, tm1, F, w, h, d, protos, A, dots, gram, tiles_y, tiles_z, ntiles, nstages);
+    kern<<<grid, 32 * (GM_CONSUMERS + 1), smem, s>>>(tm3, tm1, F, w, h, d, protos, A, dots, gram, tiles_y, tiles_z, ntiles, nstages, sa, sv);
     vittf_count_launches(1);
     return VITTF_OK;
 }
 
 // first <= 32 prototypes + Gram planes fused; prototypes beyond 32 on the dots-only tensor-core kernel
 int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const float* protos, int A, float* dots, float* gram,
-                      cudaStream_t s) {
+                      cudaStream_t s, int layout = 0) {
+    // layout 0: dots (A, n_lr); 1: (n_lr, A4) with A4 = A rounded up to 4 (the tcgen05 up-sampling kernel gathers the corner
+    // dots of 4 prototypes with one 16-byte load)
+    const int64_t n_lr = static_cast<int64_t>(w) * h * d;
+    const int64_t sa = layout ? 1 : n_lr, sv = layout ? ((A + 3) & ~3) : 1;
     CUtensorMap tm3, tm1;
     const uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint64_t>(w), static_cast<uint64_t>(F)};
     const uint64_t strides[3] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(h) * d * 2, static_cast<uint64_t>(w) * h * d * 2};
@@ -855,11 +862,11 @@ int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const flo
     VITTF_CHECK(vittf_make_tmap(&tm1, feats, 2, 4, dims, strides, box1, false));
     const int a0 = A < 32 ? A : 32;
     int rc;
-    if (a0 > 16) rc = launch_lowres_mma_one<4>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, s);
-    else if (a0 > 8) rc = launch_lowres_mma_one<2>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, s);
-    else rc = launch_lowres_mma_one<1>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, s);
+    if (a0 > 16) rc = launch_lowres_mma_one<4>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, s);
+    else if (a0 > 8) rc = launch_lowres_mma_one<2>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, s);
+    else rc = launch_lowres_mma_one<1>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, s);
     if (rc != VITTF_OK) return rc;
-    if (A > 32) VITTF_CHECK(launch_dots_mma(feats, F, static_cast<int64_t>(w) * h * d, protos, A, dots, s, 32));
+    if (A > 32) VITTF_CHECK(launch_dots_mma(feats, F, n_lr, protos, A, dots, s, 32, sa, sv));
     VITTF_CHECK_CUDA(cudaGetLastError());
     return VITTF_OK;
 }
@@ -868,7 +875,7 @@ int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const flo
 // groups of <= 32 on halo-free boxes.
 template <bool GRAM>
 int launch_lowres_tma(const __half* feats, int F, int w, int h, int d, const float* protos, int A, float* dots, float* gram,
-                      cudaStream_t s) {
+                      cudaStream_t s, int layout = 0) {
     CUtensorMap tm_halo, tm_brick;
     const uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint64_t>(w), static_cast<uint64_t>(F)};
     const uint64_t strides[3] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(h) * d * 2, static_cast<uint64_t>(w) * h * d * 2};
@@ -880,9 +887,10 @@ int launch_lowres_tma(const __half* feats, int F, int w, int h, int d, const flo
     static const bool no_mma = getenv("VITTF_SIM_NO_MMA") != nullptr;     // A/B switch: FFMA2 dots
     static const bool no_fused = getenv("VITTF_SIM_NO_FUSED") != nullptr; // A/B switch: dots (tensor cores) + Gram (FMA pipe) as two kernels
     if (!no_mma && !no_fused && F % DM_BK == 0 && d % 8 == 0) {
-        const int rc = launch_lowres_mma(feats, F, w, h, d, protos, A, dots, GRAM ? gram : nullptr, s);
+        const int rc = launch_lowres_mma(feats, F, w, h, d, protos, A, dots, GRAM ? gram : nullptr, s, layout);
         if (rc != -1) return rc;
     }
+    VITTF_REQUIRE(layout == 0, "vittf_sim_lowres: the voxel-major dots layout needs the fused tensor-core pass (fp16 features, F %% 32 == 0, d %% 8 == 0)");
     if (!no_mma && F % DM_BK == 0 && n % 8 == 0) {
         // dots of all prototypes on the tensor cores; the Gram planes (the only part that needs the halo) on the FMA pipe
         VITTF_CHECK(launch_dots_mma(feats, F, n, protos, A, dots, s));
@@ -922,17 +930,6 @@ int launch_lowres_tma(const __half* feats, int F, int w, int h, int d, const flo
 // pass 2: per output voxel.  Index rule of F.interpolate(mode='trilinear', align_corners=False):
 //   src = max((dst + 0.5) * in/out - 0.5, 0); i0 = floor(src); i1 = min(i0 + 1, in - 1); t = src - i0.
 // ---------------------------------------------------------------------------------------------
-struct UpParams {
-    const float* dots;
-    const float* gram;
-    const int* class_offsets;
-    float* out;
-    int w, h, d, A, C;
-    int W, H, D, z0, z1;
-    int mode;
-    float threshold, exponent;
-};
-
 __device__ __forceinline__ void src_index(int dst, int in, int out, int& i0, int& i1, float& t) {
     if (in == out) { i0 = i1 = dst; t = 0.0f; return; }
     const float scale = static_cast<float>(in) / static_cast<float>(out);
@@ -1983,17 +1980,26 @@ extern "C" int vittf_sample_prototypes(const void* feats, int feat_dtype, int F,
     return VITTF_OK;
 }
 
+extern "C" int vittf_sim_lowres_layout(int feat_dtype, int F, int w, int h, int d, const void* feats) {
+    static const bool off = getenv("VITTF_SIM_NO_MMA") != nullptr || getenv("VITTF_SIM_NO_FUSED") != nullptr || getenv("VITTF_SIM_NO_TMA") != nullptr;
+    const size_t panel = static_cast<size_t>(32) * (F + 8) * 2;
+    return !off && feat_dtype == VITTF_F16 && F > 0 && F % DM_BK == 0 && d % 8 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0 &&
+           static_cast<size_t>(F) * 16 * 4 <= 96 * 1024 && (220 * 1024 - panel - 256) / GM_STAGE >= 3;
+}
+
 extern "C" int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w, int h, int d, const float* protos, int A,
-                                float* dots, float* gram, void* stream) {
+                                float* dots, float* gram, int dots_layout, void* stream) {
     VITTF_REQUIRE(feats && protos && dots, "vittf_sim_lowres: null pointer");
     VITTF_REQUIRE(F > 0 && w > 0 && h > 0 && d > 0 && A > 0, "vittf_sim_lowres: empty problem");
+    VITTF_REQUIRE(dots_layout == 0 || (dots_layout == 1 && vittf_sim_lowres_layout(feat_dtype, F, w, h, d, feats)),
+                  "vittf_sim_lowres: dots_layout %d is not available for this input (ask vittf_sim_lowres_layout)", dots_layout);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (feat_dtype == VITTF_F16) {
         const __half* f = static_cast<const __half*>(feats);
         static const bool no_tma = getenv("VITTF_SIM_NO_TMA") != nullptr;     // A/B switch: previous tiled kernel
         if (!no_tma && d % 8 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 && static_cast<size_t>(F) * 16 * 4 <= 96 * 1024)
-            return gram ? launch_lowres_tma<true>(f, F, w, h, d, protos, A, dots, gram, s)
-                        : launch_lowres_tma<false>(f, F, w, h, d, protos, A, dots, gram, s);
+            return gram ? launch_lowres_tma<true>(f, F, w, h, d, protos, A, dots, gram, s, dots_layout)
+                        : launch_lowres_tma<false>(f, F, w, h, d, protos, A, dots, gram, s, dots_layout);
         if (d % 2 == 0 && (reinterpret_cast<uintptr_t>(f) & 1) == 0)   // z pairs share a 4-byte word
             return gram ? launch_lowres_tiled<true>(f, F, w, h, d, protos, A, dots, gram, s)
                         : launch_lowres_tiled<false>(f, F, w, h, d, protos, A, dots, gram, s);
@@ -2010,8 +2016,9 @@ extern "C" int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w,
 
 extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, int h, int d, int A,
                                   const int* class_offsets, int C, int W, int H, int D, int z0, int z1, int mode,
-                                  float threshold, float exponent, float* out, void* stream) {
+                                  float threshold, float exponent, int dots_layout, float* out, void* stream) {
     VITTF_REQUIRE(dots && class_offsets && out, "vittf_sim_upsample: null pointer");
+    VITTF_REQUIRE(dots_layout == 0 || dots_layout == 1, "vittf_sim_upsample: dots_layout must be 0 (A, n_lr) or 1 (n_lr, A4)");
     VITTF_REQUIRE(mode == VITTF_SIM_NS || mode == VITTF_SIM_REFNTF || mode == VITTF_SIM_LEGACY || mode == VITTF_SIM_CLAMP_MEAN,
                   "vittf_sim_upsample: unknown mode %d", mode);
     VITTF_REQUIRE(mode == VITTF_SIM_REFNTF || mode == VITTF_SIM_CLAMP_MEAN || gram, "vittf_sim_upsample: NS/LEGACY modes need the Gram planes");
@@ -2021,7 +2028,14 @@ extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, i
     // integer power-of-two up-sampling of a cubic grid, max-type modes: separable cell kernel
     const bool cubic = w == h && h == d && W == H && H == D && W % w == 0;
     const int U = cubic ? W / w : 0;
-    // any grid whose three factors are the same U in {4, 8}: tensor-core cell-tile kernel
+    // any grid whose three factors are the same U in {2, 4, 8}: tcgen05 cell-tile kernel (sim_up_tc.cu)
+    static const bool no_tc = getenv("VITTF_SIM_UP_NO_TC") != nullptr;         // A/B switch: previous mma.sync kernel
+    if (mode == VITTF_SIM_NS && (!no_tc || dots_layout == 1) && vittf_launch_upsample_tc(q, dots_layout, static_cast<cudaStream_t>(stream)) == 0) {
+        VITTF_CHECK_CUDA(cudaGetLastError());
+        vittf_count_launches(1);
+        return VITTF_OK;
+    }
+    VITTF_REQUIRE(dots_layout == 0, "vittf_sim_upsample: the voxel-major dots layout is only read by the tcgen05 kernel (NS mode, factor 2 / 4 / 8)");
     if (mode == VITTF_SIM_NS && (W == 4 * w || W == 8 * w) && H * static_cast<int64_t>(w) == static_cast<int64_t>(h) * W &&
         D * static_cast<int64_t>(w) == static_cast<int64_t>(d) * W && static_cast<int64_t>(W) * H * (z1 - z0) < (1ll << 30) &&
         static_cast<int64_t>(w) * h * d < (1ll << 31)) {

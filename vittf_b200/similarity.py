@@ -4,9 +4,14 @@ Two native passes (include/vittf.h): ``vittf_sim_lowres`` reads the feature volu
 per-voxel prototype dots (+ the 14 Gram scalars that give |interp(f)|^2), ``vittf_sim_upsample``
 evaluates every output voxel from them.  The up-sampled feature volume is never materialised.
 """
+import os
+
 import torch
 
 from . import _lib, ops
+
+TC_MAX_PROTOS = 8
+FORCE_TC = os.environ.get("VITTF_SIM_UP_TC") is not None          # A/B switch: tcgen05 up-sampling kernel for every prototype count
 
 MODES = {"ns": _lib.SIM_NS, "refntf": _lib.SIM_REFNTF, "legacy": _lib.SIM_LEGACY, "clamp_mean": _lib.SIM_CLAMP_MEAN}
 
@@ -35,7 +40,13 @@ def similarity_maps(feats, protos, offsets, out_shape=None, mode="ns", exponent=
     if m != _lib.SIM_NS and out_shape != lr:
         raise ValueError("refntf/legacy/clamp_mean similarities are defined at feature resolution")
     if lowres is None:
-        lowres = ops.sim_lowres(feats, protos, want_gram=(m not in (_lib.SIM_REFNTF, _lib.SIM_CLAMP_MEAN)))
-    dots, gram = lowres
+        # voxel-major dots where the tcgen05 up-sampling kernel will read them: NS mode, one integer factor 2 / 4 / 8, and
+        # few prototypes (measured on B200, profiles/r2_sim_kernels.md: its cost per prototype is ~3x that of the warp-level
+        # mma.sync kernel -- every prototype is a TMEM round trip -- while its fixed cost per output block is lower)
+        u = out_shape[0] // lr[0] if lr[0] else 0
+        tc = (m == _lib.SIM_NS and u in (2, 4, 8) and all(o == u * i for o, i in zip(out_shape, lr)) and out_shape[2] % 4 == 0
+              and (protos.shape[0] <= TC_MAX_PROTOS or u == 2 or FORCE_TC))
+        lowres = ops.sim_lowres(feats, protos, want_gram=(m not in (_lib.SIM_REFNTF, _lib.SIM_CLAMP_MEAN)), voxel_major=tc)
+    dots, gram, layout = lowres
     z0, z1 = (0, out_shape[2]) if z_range is None else z_range
-    return ops.sim_upsample(dots, gram, lr, offsets, out_shape, m, threshold, exponent, z0, z1)
+    return ops.sim_upsample(dots, gram, lr, offsets, out_shape, m, threshold, exponent, z0, z1, layout=layout, n_protos=protos.shape[0])
