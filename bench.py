@@ -488,19 +488,23 @@ def main():
     def step_device():
         return pipeline.volume_to_similarity(vol_dev, model, ann, 8, fos, batch, rank=rank, world=world)
 
-    feat_host = torch.empty((ARCH[arch][0],) + tuple(f_sz), dtype=torch.float16).pin_memory()
+    n_feat = ARCH[arch][0] * f_sz[0] * f_sz[1] * f_sz[2]
+    feat_share = n_feat // world if n_feat % world == 0 else n_feat               # the feature volume is replicated: every rank
+    feat_host = torch.empty(feat_share, dtype=torch.float16).pin_memory()          # brings back 1/world of it over its own link
     lab_host = maps_host = None
 
     def step_e2e():
         nonlocal lab_host, maps_host
-        v = vol_host.to(dev, non_blocking=True)                                  # H2D of the raw volume
+        v = pipeline.distribute_volume(vol_host, dev, rank, world)                # H2D of the raw volume (1/world per rank + all-gather)
         feats, sims, labels, zr = pipeline.volume_to_similarity(v, model, ann, 8, fos, batch, rank=rank, world=world)
         q, _ = pipeline.quantized_maps(sims, zr, size)                            # uint8 half-resolution maps of this rank's slab
         if lab_host is None:
             lab_host = torch.empty(labels.shape, dtype=torch.uint8).pin_memory()
             maps_host = torch.empty(q.shape, dtype=torch.uint8).pin_memory()
-        if rank == 0:
-            feat_host.copy_(feats, non_blocking=True)                           # what infer.py saves
+        if feat_share != n_feat:
+            feat_host.copy_(feats.view(-1)[rank * feat_share:(rank + 1) * feat_share], non_blocking=True)   # what infer.py saves
+        elif rank == 0:
+            feat_host.copy_(feats.view(-1), non_blocking=True)
         maps_host.copy_(q, non_blocking=True)                                    # what compute_similarities returns
         lab_host.copy_(labels, non_blocking=True)                                # the step's result
         return labels
@@ -595,8 +599,9 @@ def main():
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev, "higher_is_better": False,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": vol_host.numel(),
-                "d2h_bytes_per_step": feat_host.numel() * 2 + lab_host.numel() + maps_host.numel(),
-                "d2h_note": "rank 0: fp16 feature volume + its slab of uint8 maps and labels (every rank copies its own slab)"},
+                "d2h_bytes_per_step": n_feat * 2 + (lab_host.numel() + maps_host.numel()) * world,
+                "bytes_note": "whole job: every rank copies 1/world of the volume in and 1/world of the fp16 feature volume plus its own "
+                              "slab of uint8 maps and labels out"},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"kernel": "attention_kernel (tcgen05 flash attention, hd 64)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,

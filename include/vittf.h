@@ -108,9 +108,15 @@ int vittf_vit_timing_read(vittf_vit* v, double* ms_by_kind2, int64_t* launches_b
  * n_out == S reproduces the `_noop` pool of single-axis runs (infer.py:326).
  * accumulate != 0 adds (in fp16, rounding like infer.py:332) into `out` instead of storing.
  * Sharding: S is the GLOBAL slice count, k holds slices [slice0, slice0+n_local)
- * and only the output slabs [o0, o1) are produced (their windows must lie inside k's range). */
+ * and only the output slabs [o0, o1) are produced (their windows must lie inside k's range).
+ * compact != 0: `out` is this rank's block only, i.e. its slab axis has extent o1 - o0 (what the all-gather sends). */
 int vittf_pool_axis(const void* k_f16, int S, int slice0, int n_local, int f0, int f1, int D, int axis, int n_out,
-                    int o0, int o1, void* out_f16, int accumulate, void* stream);
+                    int o0, int o1, void* out_f16, int accumulate, int compact, void* stream);
+/* Multi-GPU merge of one slicing axis: staging fp16 (world, D, e0, e1, e2) = the all-gathered compact blocks of the ranks
+ * ((e0,e1,e2) = (fX,fY,fZ) with the slab axis -- 0 x, 1 y, 2 z -- divided by world) -> out fp16 (D,fX,fY,fZ), assigned
+ * (accumulate == 0, the first axis) or added in fp16 like infer.py:332. */
+int vittf_accumulate_gathered_f16(void* out_f16, const void* staging_f16, int world, int D, int fX, int fY, int fZ, int axis,
+                                  int accumulate, void* stream);
 
 /* out = fp16(out + in): the running sum over the three slicing axes (infer.py:332), used when
  * the per-axis volumes come from different GPUs. */

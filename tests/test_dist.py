@@ -55,6 +55,12 @@ def _worker(rank, world, port, out):
             dst[1 + s_dim] = slice(o0, o1)
             buf[tuple(dst)] = F.adaptive_avg_pool3d(full[tuple(src)], tuple(tgt))
         dist.all_reduce_disjoint(buf)
+        # the all-gather formulation of the same exchange: compact blocks, rank-major staging, un-permute
+        assert dist.even_slabs(n_out, world)
+        blk = [slice(None)] * 4
+        blk[1 + s_dim] = slice(o0, o1)
+        staging, _ = dist.gather_blocks(buf[tuple(blk)].contiguous())
+        assert torch.equal(dist.unpermute_gathered(staging, ax), buf)
         acc = buf if acc is None else acc + buf
     if rank == 0:
         torch.save(acc, out)

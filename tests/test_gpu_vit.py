@@ -62,6 +62,34 @@ def test_pool_axis_matches_adaptive_avg_pool(axis, shape, n_out):
         assert torch.equal(part, want)
 
 
+@pytest.mark.parametrize("axis", ["z", "y", "x"])
+@pytest.mark.parametrize("shape,world", [((16, 8, 16), 2), ((6, 9, 12), 3), ((64, 64, 64), 8), ((5, 7, 8), 1)])
+def test_gathered_merge_matches_the_layout_rule(axis, shape, world):
+    """Multi-GPU merge: pooling into a rank's compact block + the un-permuting fp16 accumulate of the
+    all-gathered blocks == pooling into the full array, bit-exactly (vector and scalar paths, assign and add)."""
+    from vittf_b200 import dist, ops
+    f0, f1, n_out = shape
+    if n_out % world:
+        pytest.skip("uneven slabs use the all-reduce path")
+    D, S = 64, 2 * n_out
+    k = torch.randn(S, f0 * f1, D, device="cuda").half()
+    full = ops.pool_axis(k, f0, f1, axis, n_out)
+    blocks = []
+    for r in range(world):
+        o0, o1 = dist.slab_range(n_out, world, r)
+        a, b = dist.slices_for_slabs(S, n_out, o0, o1)
+        blocks.append(ops.pool_axis(k[a:b].contiguous(), f0, f1, axis, n_out, total_slices=S, slice0=a, slabs=(o0, o1), compact=True))
+    staging = torch.stack(blocks)
+    assert torch.equal(dist.unpermute_gathered(staging, axis), full)
+    out = torch.empty_like(full)
+    ops.accumulate_gathered(out, staging, axis, accumulate=False)
+    assert torch.equal(out, full)
+    base = torch.randn_like(full)
+    want = (base.float() + full.float()).half()
+    ops.accumulate_gathered(base, staging, axis, accumulate=True)
+    assert torch.equal(base, want)
+
+
 def _oracle_tokens(model, vol, axis, im_sz):
     from oracle import feature_volume as fv
     imgs = fv.slice_images(vol, axis)

@@ -52,7 +52,8 @@ _SIGNATURES = {
     "vittf_vit_destroy": (None, [_p]),
     "vittf_vit_workspace_bytes": (_i64, [_p, _i, _i]),
     "vittf_vit_k_features": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _p]),
-    "vittf_pool_axis": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "vittf_pool_axis": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "vittf_accumulate_gathered_f16": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "vittf_accumulate_f16": (_i, [_p, _p, _i64, _p]),
     "vittf_gemm_bf16": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vittf_attention": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),

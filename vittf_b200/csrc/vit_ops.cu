@@ -447,6 +447,7 @@ struct PoolParams {
     __half* out;
     int S, T, D, n_out;
     int slice0, n_local, o0;   // k holds global slices [slice0, slice0+n_local); blockIdx.z + o0 = output slab
+    int out_o0;                // slab index of the output array's first slab (0: full-size array, o0: compact block of this rank)
     int f1;
     int64_t sd, s0, s1, so;  // output strides (elements) of d, i0, i1, o
     int accumulate;
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(256) pool_axis_kernel(PoolParams q) {
     const int t = t0 + tl;
     if (t >= q.T) return;
     const int i0 = t / q.f1, i1 = t - i0 * q.f1;
-    const int64_t base = i0 * q.s0 + i1 * q.s1 + o * q.so;
+    const int64_t base = i0 * q.s0 + i1 * q.s1 + (o - q.out_o0) * q.so;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int dl = (threadIdx.x >> 5) + 8 * r;
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(256) pool_axis_z_kernel(PoolParams q, int o_en
         const int t = t0 + tl;
         if (t >= q.T || d0 + dl >= q.D) continue;
         const int i0 = t / q.f1, i1 = t - i0 * q.f1;
-        __half* dst = q.out + (d0 + dl) * q.sd + i0 * q.s0 + i1 * q.s1 + ob;      // so == 1
+        __half* dst = q.out + (d0 + dl) * q.sd + i0 * q.s0 + i1 * q.s1 + (ob - q.out_o0);      // so == 1
         __half v[POOLZ_OB];
 #pragma unroll
         for (int oo = 0; oo < POOLZ_OB; ++oo) v[oo] = tile[oo][tl][dl];
@@ -597,7 +598,69 @@ __global__ void __launch_bounds__(256) accumulate_f16_kernel(__half* __restrict_
         for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = __hadd(out[i], in[i]);
 }
 
+// Multi-GPU merge: the all-gather of the ranks' compact per-axis blocks lands rank-major, (world, D, e0, e1, e2)
+// with the slab axis extent divided by `world`; this kernel un-permutes it into (D, fX, fY, fZ) on the fly and either
+// assigns (first axis: fp16(0 + z) = z) or adds in fp16 (infer.py:332), VEC halves along z per thread.
+template <int VEC>
+__global__ void __launch_bounds__(256) accumulate_gathered_kernel(__half* __restrict__ out, const __half* __restrict__ st, int world, int D,
+                                                                  int fX, int fY, int fZ, int axis, int accumulate) {
+    const int64_t n = static_cast<int64_t>(D) * fX * fY * fZ / VEC;
+    const int zv = fZ / VEC;
+    const int nloc = (axis == 2 ? fZ : axis == 1 ? fY : fX) / world;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int z = static_cast<int>(i % zv) * VEC;
+        int64_t t = i / zv;
+        const int y = static_cast<int>(t % fY);
+        t /= fY;
+        const int x = static_cast<int>(t % fX);
+        const int d = static_cast<int>(t / fX);
+        int64_t src;
+        if (axis == 2) { const int r = z / nloc; src = (((static_cast<int64_t>(r) * D + d) * fX + x) * fY + y) * nloc + (z - r * nloc); }
+        else if (axis == 1) { const int r = y / nloc; src = (((static_cast<int64_t>(r) * D + d) * fX + x) * nloc + (y - r * nloc)) * fZ + z; }
+        else { const int r = x / nloc; src = (((static_cast<int64_t>(r) * D + d) * nloc + (x - r * nloc)) * fY + y) * fZ + z; }
+        if (VEC == 8) {
+            uint4 b = __ldg(reinterpret_cast<const uint4*>(st + src));
+            if (accumulate) {
+                const uint4 a = *reinterpret_cast<const uint4*>(out + i * 8);
+                const __half2* ah = reinterpret_cast<const __half2*>(&a);
+                __half2* bh = reinterpret_cast<__half2*>(&b);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) bh[k] = __hadd2(ah[k], bh[k]);
+            }
+            *reinterpret_cast<uint4*>(out + i * 8) = b;
+        } else {
+            const __half b = st[src];
+            out[i] = accumulate ? __hadd(out[i], b) : b;
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int vittf_accumulate_gathered_f16(void* out_f16, const void* staging_f16, int world, int D, int fX, int fY, int fZ, int axis,
+                                             int accumulate, void* stream) {
+    VITTF_REQUIRE(out_f16 && staging_f16, "vittf_accumulate_gathered_f16: null pointer");
+    VITTF_REQUIRE(world > 0 && D > 0 && fX > 0 && fY > 0 && fZ > 0 && axis >= 0 && axis <= 2, "vittf_accumulate_gathered_f16: bad sizes");
+    const int ext = axis == 2 ? fZ : axis == 1 ? fY : fX;
+    VITTF_REQUIRE(ext % world == 0, "vittf_accumulate_gathered_f16: %d slabs do not divide over %d ranks", ext, world);
+    const int nloc = ext / world;
+    const bool vec = fZ % 8 == 0 && (axis != 2 || nloc % 8 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out_f16) | reinterpret_cast<uintptr_t>(staging_f16)) & 15) == 0;
+    const int64_t n = static_cast<int64_t>(D) * fX * fY * fZ / (vec ? 8 : 1);
+    int64_t blocks = ceil_div_ll(n, 256);
+    const int64_t cap = static_cast<int64_t>(vittf_num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (vec)
+        accumulate_gathered_kernel<8><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<__half*>(out_f16), static_cast<const __half*>(staging_f16),
+                                                                                    world, D, fX, fY, fZ, axis, accumulate);
+    else
+        accumulate_gathered_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, s>>>(static_cast<__half*>(out_f16), static_cast<const __half*>(staging_f16),
+                                                                                    world, D, fX, fY, fZ, axis, accumulate);
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
 
 extern "C" int vittf_accumulate_f16(void* out_f16, const void* in_f16, int64_t n, void* stream) {
     VITTF_REQUIRE(out_f16 && in_f16 && n > 0, "vittf_accumulate_f16: bad arguments");
@@ -744,7 +807,7 @@ extern "C" int vittf_layernorm(const float* x, const float* w, const float* b, v
 }
 
 extern "C" int vittf_pool_axis(const void* k_f16, int S, int slice0, int n_local, int f0, int f1, int D, int axis,
-                               int n_out, int o0, int o1, void* out_f16, int accumulate, void* stream) {
+                               int n_out, int o0, int o1, void* out_f16, int accumulate, int compact, void* stream) {
     VITTF_REQUIRE(k_f16 && out_f16, "vittf_pool_axis: null pointer");
     // n_out > S is legal (AdaptiveAvgPool3d replicates slices: every window [floor(o*S/n), ceil((o+1)*S/n)) is non-empty)
     VITTF_REQUIRE(S > 0 && f0 > 0 && f1 > 0 && D > 0 && n_out > 0, "vittf_pool_axis: bad sizes");
@@ -763,14 +826,17 @@ extern "C" int vittf_pool_axis(const void* k_f16, int S, int slice0, int n_local
     q.out = static_cast<__half*>(out_f16);
     q.S = S; q.T = f0 * f1; q.D = D; q.n_out = n_out; q.f1 = f1; q.accumulate = accumulate;
     q.slice0 = slice0; q.n_local = n_local; q.o0 = o0;
-    // output (D, A, B, C) contiguous; which of A,B,C are i0 / i1 / o depends on the slicing axis
+    // output (D, A, B, C) contiguous; which of A,B,C are i0 / i1 / o depends on the slicing axis.  compact: the array holds
+    // only the slabs [o0, o1) of this rank (the block the all-gather of the multi-GPU path sends)
+    q.out_o0 = compact ? o0 : 0;
+    const int ext = compact ? o1 - o0 : n_out;
     int64_t A, B, C;
-    if (axis == 2) { A = f0; B = f1; C = n_out; q.s0 = B * C; q.s1 = C; q.so = 1; }          // (D, fX, fY, o)
-    else if (axis == 1) { A = f0; B = n_out; C = f1; q.s0 = B * C; q.so = C; q.s1 = 1; }     // (D, fX, o, fZ)
-    else { A = n_out; B = f0; C = f1; q.so = B * C; q.s0 = C; q.s1 = 1; }                    // (D, o, fY, fZ)
+    if (axis == 2) { A = f0; B = f1; C = ext; q.s0 = B * C; q.s1 = C; q.so = 1; }          // (D, fX, fY, o)
+    else if (axis == 1) { A = f0; B = ext; C = f1; q.s0 = B * C; q.so = C; q.s1 = 1; }     // (D, fX, o, fZ)
+    else { A = ext; B = f0; C = f1; q.so = B * C; q.s0 = C; q.s1 = 1; }                    // (D, o, fY, fZ)
     q.sd = A * B * C;
     dim3 grid(ceil_div(q.T, 32), ceil_div(D, 64), o1 - o0);
-    if (axis == 2 && n_out % POOLZ_OB == 0 && o0 % POOLZ_OB == 0 && (reinterpret_cast<uintptr_t>(out_f16) & 15) == 0) {
+    if (axis == 2 && ext % POOLZ_OB == 0 && (o0 - q.out_o0) % POOLZ_OB == 0 && (reinterpret_cast<uintptr_t>(out_f16) & 15) == 0) {
         grid.z = ceil_div(o1 - o0, POOLZ_OB);
         pool_axis_z_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, o1);
     } else {

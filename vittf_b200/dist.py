@@ -5,9 +5,12 @@ for the plumbing.  Pure planning functions (no CUDA needed) + the one collective
     slabs and therefore the slices inside those slabs' AdaptiveAvgPool windows
     ``[floor(o*S/n), ceil((o+1)*S/n))`` -- disjoint whenever S % n == 0, otherwise neighbouring ranks
     both evaluate the shared boundary slice (reads only, no exchange).
-  * Each rank writes its slabs into a zero-initialised full-size per-axis buffer; ONE all-reduce(sum)
-    per axis assembles the volume.  Supports are disjoint, so every element is x + 0 + ... + 0: exact
-    in fp16 in any reduction order.  The z, y, x buffers are then summed in the reference's order.
+  * When the pooled slabs divide evenly over the ranks, each rank pools into a COMPACT block (its slabs only) and ONE
+    all-gather per axis moves exactly the bytes that are needed; it is launched asynchronously, so the exchange of
+    one axis runs under the ViT compute of the next, and a native kernel un-permutes the rank-major result while it
+    sums the axes in the reference's order (z, y, x, fp16).  Otherwise (uneven slabs) each rank writes into a
+    zero-initialised full-size buffer and ONE all-reduce(sum) per axis assembles the volume: supports are disjoint,
+    so every element is x + 0 + ... + 0, exact in fp16 in any reduction order.
   * Similarity / labels shard over z-slabs of the OUTPUT grid; with the feature volume replicated by
     the all-reduce above there is no halo exchange.
 """
@@ -37,3 +40,30 @@ def all_reduce_disjoint(buf, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return buf
+
+
+def even_slabs(n_out, world):
+    """True when every rank owns the same number (> 0) of pooled slabs: the all-gather path applies."""
+    return world > 1 and n_out % world == 0
+
+
+def gather_blocks(block, group=None, async_op=False):
+    """All-gather of the ranks' compact per-axis blocks: returns (staging (world, *block.shape), work handle or None)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    staging = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
+    if dist.get_backend(group) == "nccl":
+        work = dist.all_gather_into_tensor(staging, block.contiguous(), group=group, async_op=async_op)
+    else:                                                   # gloo (CPU tests): no flat-tensor form for every dtype
+        work = dist.all_gather([staging[r] for r in range(world)], block.contiguous(), group=group, async_op=async_op)
+    return staging, work
+
+
+def unpermute_gathered(staging, axis):
+    """The layout rule of the merge in plain tensor ops (planning reference for the CPU tests and the parity check of
+    vittf_accumulate_gathered_f16): staging (world, D, e0, e1, e2) with the slab axis split over ranks -> (D, fX, fY, fZ)."""
+    dim = {"x": 1, "y": 2, "z": 3}[axis]                      # slab axis inside one (D, e0, e1, e2) block
+    blocks = [staging[r] for r in range(staging.shape[0])]
+    import torch
+    return torch.cat(blocks, dim=dim)

@@ -155,10 +155,11 @@ def _pool_target(pool_fn, axis, n_slices, f_sz3):
     return None
 
 
-def k_features_axis_device(vol_dev, engine, im_sizes, slice_along, batch_size, n_out, mm=None, rank=0, world=1):
+def k_features_axis_device(vol_dev, engine, im_sizes, slice_along, batch_size, n_out, mm=None, rank=0, world=1, compact=False):
     """Device-resident core of compute_qkv: per-axis K features pooled to `n_out` slabs along the slice
     axis, in the reference layout (D, ., ., .).  With world > 1 this rank evaluates only the slices of
-    its slab range (vittf_b200/dist.py) and the returned buffer is zero elsewhere."""
+    its slab range (vittf_b200/dist.py); the returned buffer is full-size and zero elsewhere, or with
+    compact=True holds this rank's slabs only (the block the all-gather sends)."""
     from . import dist
     r, c = AXIS_IMAGE_DIMS[slice_along]
     s_dim = AXIS_SLICE_DIM[slice_along]
@@ -170,16 +171,17 @@ def k_features_axis_device(vol_dev, engine, im_sizes, slice_along, batch_size, n
         mm = ops.minmax(vol_dev)
     o0, o1 = dist.slab_range(n_out, world, rank)
     a, b = dist.slices_for_slabs(S, n_out, o0, o1)
-    shape = {"z": (engine.embed_dim, f0, f1, n_out), "y": (engine.embed_dim, f0, n_out, f1),
-             "x": (engine.embed_dim, n_out, f0, f1)}[slice_along]
-    alloc = torch.empty if world == 1 else torch.zeros
+    ext = o1 - o0 if compact else n_out
+    shape = {"z": (engine.embed_dim, f0, f1, ext), "y": (engine.embed_dim, f0, ext, f1),
+             "x": (engine.embed_dim, ext, f0, f1)}[slice_along]
+    alloc = torch.empty if (world == 1 or compact) else torch.zeros
     out = alloc(shape, dtype=torch.float16, device=vol_dev.device)
     if b > a:
         kbuf = torch.empty(b - a, f0 * f1, engine.embed_dim, dtype=torch.float16, device=vol_dev.device)
         for s0 in range(a, b, batch_size):
             s1 = min(b, s0 + batch_size)
             engine.k_features(vol_dev, slice_along, s0, s1, im0, im1, mm, out=kbuf[s0 - a:s1 - a])
-        ops.pool_axis(kbuf, f0, f1, slice_along, n_out, out=out, total_slices=S, slice0=a, slabs=(o0, o1))
+        ops.pool_axis(kbuf, f0, f1, slice_along, n_out, out=out, total_slices=S, slice0=a, slabs=(o0, o1), compact=compact)
     return out
 
 
@@ -225,8 +227,9 @@ def feature_volume(vol, model, patch_size=8, feature_output_size=64, batch_size=
                    rank=0, world=1, group=None):
     """The 3-axis loop of infer.py:327-333 with everything kept on the device: returns the merged fp16
     feature volume (D, fX, fY, fZ) as a CUDA tensor (z, then y, then x summed in fp16).  With world > 1
-    the slices of every axis are sharded over the ranks and one all-reduce per axis assembles the
-    (replicated) result."""
+    the slices of every axis are sharded over the ranks; one all-gather per axis (asynchronous: it runs under the
+    next axis' ViT compute) assembles the replicated result, un-permuted and summed by a native kernel -- or one
+    all-reduce per axis when the pooled slabs do not divide evenly over the ranks."""
     from . import dist
     dev = _cuda_device(dev)
     v = vol.squeeze().to(dev)
@@ -238,13 +241,41 @@ def feature_volume(vol, model, patch_size=8, feature_output_size=64, batch_size=
     mm = ops.minmax(v)
     out = None
     axes = ['z', 'y', 'x'] if slice_along == 'all' else [slice_along]
+    pending = None                                        # (work, staging, axis) of the exchange in flight
+
+    def finish(pending, out):
+        work, staging, ax = pending
+        work.wait()                                        # the current stream waits for the collective
+        if out is None:
+            out = torch.empty((staging.shape[1],) + tuple(full_shape[ax]), dtype=torch.float16, device=dev)
+            return ops.accumulate_gathered(out, staging, ax, accumulate=False)
+        return ops.accumulate_gathered(out, staging, ax, accumulate=True)
+
+    full_shape = {}
     with torch.no_grad():
         for ax in axes:
-            n_out = f_sz[AXIS_SLICE_DIM[ax]] if slice_along == 'all' else v.shape[AXIS_SLICE_DIM[ax]]
+            s_dim = AXIS_SLICE_DIM[ax]
+            n_out = f_sz[s_dim] if slice_along == 'all' else v.shape[s_dim]
+            r_, c_ = AXIS_IMAGE_DIMS[ax]
+            fs = [0, 0, 0]
+            fs[r_], fs[c_], fs[s_dim] = im_sz[r_] // patch_size, im_sz[c_] // patch_size, n_out
+            full_shape[ax] = tuple(fs)
+            if dist.even_slabs(n_out, world):
+                block = k_features_axis_device(v, engine, im_sz, ax, batch_size, n_out, mm=mm, rank=rank, world=world, compact=True)
+                if pending is not None:                   # the previous axis' exchange ran under this axis' ViT compute
+                    out = finish(pending, out)
+                staging, work = dist.gather_blocks(block, group, async_op=True)
+                pending = (work, staging, ax)
+                continue
             part = k_features_axis_device(v, engine, im_sz, ax, batch_size, n_out, mm=mm, rank=rank, world=world)
+            if pending is not None:
+                out = finish(pending, out)
+                pending = None
             if world > 1:
                 dist.all_reduce_disjoint(part, group)
             out = part if out is None else ops.accumulate_f16(out, part)
+        if pending is not None:
+            out = finish(pending, out)
     return out
 
 

@@ -116,22 +116,36 @@ def patch_embed(vol, axis, s0, s1, im0, im1, patch, mm, patch_w, patch_b, pos):
 
 
 @_on_device
-def pool_axis(k, f0, f1, axis, n_out, out=None, accumulate=False, total_slices=None, slice0=0, slabs=None):
+def pool_axis(k, f0, f1, axis, n_out, out=None, accumulate=False, total_slices=None, slice0=0, slabs=None, compact=False):
     """k (S, f0*f1, D) fp16 -> (D, ., ., .) fp16 in the reference layout (infer.py:203).
     Sharded use: k holds global slices [slice0, slice0+S) of `total_slices`; only output slabs
-    `slabs=(o0, o1)` are written."""
+    `slabs=(o0, o1)` are written -- into the full-size array, or with compact=True into this rank's
+    block whose slab axis has extent o1 - o0 (what the multi-GPU all-gather sends)."""
     require_cuda(k, out)
     n_local, T, D = k.shape
     S = n_local if total_slices is None else total_slices
     o0, o1 = (0, n_out) if slabs is None else slabs
     assert T == f0 * f1
-    shape = {"z": (D, f0, f1, n_out), "y": (D, f0, n_out, f1), "x": (D, n_out, f0, f1)}[axis]
+    ext = o1 - o0 if compact else n_out
+    shape = {"z": (D, f0, f1, ext), "y": (D, f0, ext, f1), "x": (D, ext, f0, f1)}[axis]
     if out is None:
         assert not accumulate
         out = torch.empty(shape, dtype=torch.float16, device=k.device)
     assert tuple(out.shape) == shape and out.dtype == torch.float16
     check(load().vittf_pool_axis(ptr(k), S, slice0, n_local, f0, f1, D, AXIS_INDEX[axis], n_out, o0, o1, ptr(out),
-                                 int(accumulate), stream_ptr(k.device)), "vittf_pool_axis")
+                                 int(accumulate), int(compact), stream_ptr(k.device)), "vittf_pool_axis")
+    return out
+
+
+@_on_device
+def accumulate_gathered(out, staging, axis, accumulate):
+    """out fp16 (D,fX,fY,fZ) = (or +=, in fp16) the un-permuted all-gather `staging` (world, D, e0, e1, e2) of one axis."""
+    require_cuda(out, staging)
+    D, fX, fY, fZ = out.shape
+    world = staging.shape[0]
+    assert out.dtype == staging.dtype == torch.float16 and staging.numel() == out.numel()
+    check(load().vittf_accumulate_gathered_f16(ptr(out), ptr(staging), world, D, fX, fY, fZ, AXIS_INDEX[axis], int(accumulate),
+                                               stream_ptr(out.device)), "vittf_accumulate_gathered_f16")
     return out
 
 

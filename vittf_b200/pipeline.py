@@ -35,6 +35,21 @@ def volume_to_similarity(vol_dev, model, annotations, patch=8, fos=64, batch_siz
     return feats, sims, labels, zr
 
 
+def distribute_volume(vol_host, dev, rank=0, world=1, group=None):
+    """Host -> devices: the replicated raw volume every rank slices along all three axes.  With several ranks each one
+    copies 1/world of the (pinned) bytes over its own PCIe link and ONE all-gather over NVLink assembles the copies --
+    instead of `world` full host reads (broadcast once)."""
+    import torch.distributed as td
+    n = vol_host.numel()
+    if world == 1 or n % world or not (td.is_available() and td.is_initialized()):
+        return vol_host.to(dev, non_blocking=True)
+    flat = vol_host.reshape(-1)
+    part = flat[rank * (n // world):(rank + 1) * (n // world)].to(dev, non_blocking=True)
+    full = torch.empty(n, dtype=vol_host.dtype, device=dev)
+    td.all_gather_into_tensor(full, part, group=group)
+    return full.view(vol_host.shape)
+
+
 def quantized_maps(sims_slab, z_range, depth, group=None):
     """The uint8 maps compute_similarities hands back (predict_ntf.py:95-100: 0.99*max quantisation with the
     reference's wrap, nearest-resized to half the grid) for this rank's z-slab of fp32 maps (C,W,H,z1-z0).  The class
