@@ -97,102 +97,227 @@ __global__ void __launch_bounds__(256) splat_kernel(Grid g, int z0, int zs, cons
     }
 }
 
-// ---- blur of an occupied-masked vector -----------------------------------------------------------------
-__device__ __forceinline__ double blur_at(const Grid& g, const double* __restrict__ y, int64_t j) {
-    const int l = static_cast<int>(j % g.L);
-    const int64_t s = j / g.L;
-    const int cz = static_cast<int>(s % g.gz), cy = static_cast<int>((s / g.gz) % g.gy), cx = static_cast<int>(s / (static_cast<int64_t>(g.gz) * g.gy));
+// =========================================================================================================
+// Grid stage on the OCCUPIED cells only.  The dense (gx, gy, gz, L) box is ~80 % empty (a 7^3-voxel spatial bin touches
+// a handful of its 52 luma bins), and with 8 right-hand sides the 25 PCG iterations stream ~110 grid vectors each:
+// on the dense box that is HBM traffic nobody needs (146 ms at 512^3).  So, like the reference's np.unique vertex set
+// (:60-61) but without a sort: the occupancy mask is compacted by a prefix sum (dense order is kept), every vertex gets its 8
+// lattice neighbours as compact indices (:71-81, -1 = missing), and all solver vectors live in compact, right-hand-side-
+// interleaved form [vertex][KP] (KP = nrhs rounded up to a power of two): per-vertex scalars and the neighbour table are
+// read once for all right-hand sides, a neighbour gather is one contiguous 8 * KP-byte piece, and one thread = one
+// (vertex, rhs) pair.  The arithmetic per cell is the dense formulation's, term for term.
+// =========================================================================================================
+constexpr int SCAN_BLOCK = 1024;         // cells per scan block (256 threads x 4)
+
+__global__ void __launch_bounds__(256) occ_count_kernel(int64_t ncell, const double* __restrict__ m_cnt, int* __restrict__ block_sums) {
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * SCAN_BLOCK;
+    int c = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int64_t j = base + u * 256 + threadIdx.x;
+        c += (j < ncell && m_cnt[j] > 0.0) ? 1 : 0;
+    }
+    c = __syncthreads_count(c & 1) + 2 * __syncthreads_count(c & 2) + 4 * __syncthreads_count(c & 4);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = c;
+}
+// exclusive scan of the block sums in place (one CTA), total -> *nv
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(int* __restrict__ block_sums, int nblocks, int* __restrict__ nv) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? block_sums[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;                                   // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + (wid > 0 ? warp_tot[wid - 1] : 0) + incl - v;
+        if (i < nblocks) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nv = carry_s;
+}
+// idx_map[dense] = compact index or -1; cells[compact] = dense index (dense order preserved)
+__global__ void __launch_bounds__(256) compact_kernel(int64_t ncell, const double* __restrict__ m_cnt, const int* __restrict__ block_sums,
+                                                      int* __restrict__ idx_map, int* __restrict__ cells) {
+    __shared__ int warp_cnt[8];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * SCAN_BLOCK;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int run = block_sums[blockIdx.x];
+    for (int u = 0; u < 4; ++u) {
+        const int64_t j = base + u * 256 + threadIdx.x;
+        const bool occ = j < ncell && m_cnt[j] > 0.0;
+        const unsigned bal = __ballot_sync(0xffffffffu, occ);
+        if (lane == 0) warp_cnt[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            before += w < wid ? warp_cnt[w] : 0;
+            total += warp_cnt[w];
+        }
+        const int v = run + before + __popc(bal & ((1u << lane) - 1u));
+        if (j < ncell) idx_map[j] = occ ? v : -1;
+        if (occ) cells[v] = static_cast<int>(j);
+        run += total;
+        __syncthreads();
+    }
+}
+// neighbour table in the blur's summation order: l-1, l+1, z-1, z+1, y-1, y+1, x-1, x+1; plus the per-vertex counts
+__global__ void __launch_bounds__(256) neighbours_kernel(Grid g, const int* __restrict__ nv_p, const int* __restrict__ cells,
+                                                         const int* __restrict__ idx_map, const double* __restrict__ acc,
+                                                         int* __restrict__ nbr, double* __restrict__ m_cnt_c, double* __restrict__ wbar_c) {
+    const int nv = *nv_p;
     const int64_t sz = g.L, sy = static_cast<int64_t>(g.gz) * g.L, sx = static_cast<int64_t>(g.gy) * g.gz * g.L;
-    double acc = 12.0 * y[j];   // 2 * dim with dim = 6 lattice dimensions (:96)
-    if (l > 0) acc += y[j - 1];
-    if (l < g.L - 1) acc += y[j + 1];
-    if (cz > 0) acc += y[j - sz];
-    if (cz < g.gz - 1) acc += y[j + sz];
-    if (cy > 0) acc += y[j - sy];
-    if (cy < g.gy - 1) acc += y[j + sy];
-    if (cx > 0) acc += y[j - sx];
-    if (cx < g.gx - 1) acc += y[j + sx];
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+        const int64_t j = cells[v];
+        const int l = static_cast<int>(j % g.L);
+        const int64_t s = j / g.L;
+        const int cz = static_cast<int>(s % g.gz), cy = static_cast<int>((s / g.gz) % g.gy), cx = static_cast<int>(s / (static_cast<int64_t>(g.gz) * g.gy));
+        int* nb = nbr + static_cast<int64_t>(v) * 8;
+        nb[0] = l > 0 ? idx_map[j - 1] : -1;
+        nb[1] = l < g.L - 1 ? idx_map[j + 1] : -1;
+        nb[2] = cz > 0 ? idx_map[j - sz] : -1;
+        nb[3] = cz < g.gz - 1 ? idx_map[j + sz] : -1;
+        nb[4] = cy > 0 ? idx_map[j - sy] : -1;
+        nb[5] = cy < g.gy - 1 ? idx_map[j + sy] : -1;
+        nb[6] = cx > 0 ? idx_map[j - sx] : -1;
+        nb[7] = cx < g.gx - 1 ? idx_map[j + sx] : -1;
+        m_cnt_c[v] = acc[j];
+        wbar_c[v] = acc[g.ncell + j];
+    }
+}
+// blur of a compact scalar vector: 12 y + sum over existing neighbours (:93-99, 2 * dim with dim = 6)
+__device__ __forceinline__ double blur1(const double* __restrict__ y, const int* __restrict__ nb, int v) {
+    double acc = 12.0 * y[v];
+    const int4 a = *reinterpret_cast<const int4*>(nb), b = *reinterpret_cast<const int4*>(nb + 4);
+    if (a.x >= 0) acc += y[a.x];
+    if (a.y >= 0) acc += y[a.y];
+    if (a.z >= 0) acc += y[a.z];
+    if (a.w >= 0) acc += y[a.w];
+    if (b.x >= 0) acc += y[b.x];
+    if (b.y >= 0) acc += y[b.y];
+    if (b.z >= 0) acc += y[b.z];
+    if (b.w >= 0) acc += y[b.w];
     return acc;
 }
-
-__global__ void __launch_bounds__(256) occ_init_kernel(int64_t ncell, const double* __restrict__ m, double* __restrict__ n) {
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < ncell;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x)
-        n[j] = m[j] > 0.0 ? 1.0 : 0.0;
+__global__ void __launch_bounds__(256) fill_ones_kernel(const int* __restrict__ nv_p, double* __restrict__ n) {
+    const int nv = *nv_p;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) n[v] = 1.0;
 }
-// n_out = sqrt(n * m / blur(n)) on occupied cells (:111-112)
-__global__ void __launch_bounds__(256) bistoch_step_kernel(Grid g, const double* __restrict__ m, const double* __restrict__ n_in,
-                                                           double* __restrict__ n_out) {
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < g.ncell;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x)
-        n_out[j] = m[j] > 0.0 ? sqrt(n_in[j] * m[j] / blur_at(g, n_in, j)) : 0.0;
+// n_out = sqrt(n * m / blur(n)) (:111-112)
+__global__ void __launch_bounds__(256) bistoch_step_kernel(const int* __restrict__ nv_p, const int* __restrict__ nbr, const double* __restrict__ m_cnt,
+                                                           const double* __restrict__ n_in, double* __restrict__ n_out) {
+    const int nv = *nv_p;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x)
+        n_out[v] = sqrt(n_in[v] * m_cnt[v] / blur1(n_in, nbr + static_cast<int64_t>(v) * 8, v));
 }
 // m' = n * blur(n) (:115); Minv = 1 / max(lam (m' - 12 n^2) + wbar, diag_min) (:141-142)
-__global__ void __launch_bounds__(256) bistoch_finish_kernel(Grid g, const double* __restrict__ m_cnt, const double* __restrict__ n,
+__global__ void __launch_bounds__(256) bistoch_finish_kernel(const int* __restrict__ nv_p, const int* __restrict__ nbr, const double* __restrict__ n,
                                                              const double* __restrict__ wbar, double lam, double diag_min,
                                                              double* __restrict__ m_out, double* __restrict__ minv) {
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < g.ncell;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const bool occ = m_cnt[j] > 0.0;
-        const double mm = occ ? n[j] * blur_at(g, n, j) : 0.0;
-        m_out[j] = mm;
-        minv[j] = occ ? 1.0 / fmax(lam * (mm - 12.0 * n[j] * n[j]) + wbar[j], diag_min) : 0.0;
+    const int nv = *nv_p;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+        const double mm = n[v] * blur1(n, nbr + static_cast<int64_t>(v) * 8, v);
+        m_out[v] = mm;
+        minv[v] = 1.0 / fmax(lam * (mm - 12.0 * n[v] * n[v]) + wbar[v], diag_min);
     }
 }
 
-// ---- block reduction helper: adds `v` (and optionally `u`) into device doubles -------------------------
-__device__ __forceinline__ void block_add2(double v, double u, double* dst_v, double* dst_u) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        v += __shfl_xor_sync(0xffffffffu, v, o);
-        u += __shfl_xor_sync(0xffffffffu, u, o);
-    }
-    __shared__ double sv[8], su[8];
-    const int wdx = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { sv[wdx] = v; su[wdx] = u; }
+// ---- per-right-hand-side block reduction: thread t holds the partial sums of rhs k = t & (KP - 1) --------------------
+__device__ __forceinline__ void block_add_rhs(double v, double u, int KP, int nrhs, RhsScalars* sc, int which) {
+    __shared__ double sv[256], su[256];
+    sv[threadIdx.x] = v;
+    su[threadIdx.x] = u;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) { v += sv[i]; u += su[i]; }
-        atomicAdd(dst_v, v);
-        if (dst_u) atomicAdd(dst_u, u);
+    if (static_cast<int>(threadIdx.x) < KP && static_cast<int>(threadIdx.x) < nrhs) {
+        double a = 0.0, b = 0.0;
+        for (int i = threadIdx.x; i < 256; i += KP) { a += sv[i]; b += su[i]; }
+        RhsScalars& s = sc[threadIdx.x];
+        if (which == 0) atomicAdd(&s.bb, a);
+        else if (which == 1) { atomicAdd(&s.rr_next, a); atomicAdd(&s.rho_next, b); }
+        else atomicAdd(&s.pq, a);
     }
+    __syncthreads();
 }
+// blur of an interleaved vector for right-hand side k
+__device__ __forceinline__ double blurk(const double* __restrict__ y, const int* __restrict__ nb, int64_t self, int kshift, int k) {
+    double acc = 12.0 * y[self];
+    const int4 a = *reinterpret_cast<const int4*>(nb), b = *reinterpret_cast<const int4*>(nb + 4);
+    if (a.x >= 0) acc += y[(static_cast<int64_t>(a.x) << kshift) + k];
+    if (a.y >= 0) acc += y[(static_cast<int64_t>(a.y) << kshift) + k];
+    if (a.z >= 0) acc += y[(static_cast<int64_t>(a.z) << kshift) + k];
+    if (a.w >= 0) acc += y[(static_cast<int64_t>(a.w) << kshift) + k];
+    if (b.x >= 0) acc += y[(static_cast<int64_t>(b.x) << kshift) + k];
+    if (b.y >= 0) acc += y[(static_cast<int64_t>(b.y) << kshift) + k];
+    if (b.z >= 0) acc += y[(static_cast<int64_t>(b.z) << kshift) + k];
+    if (b.w >= 0) acc += y[(static_cast<int64_t>(b.w) << kshift) + k];
+    return acc;
+}
+// Items i = (vertex << kshift) + k walk the interleaved vectors contiguously; the grid stride is a multiple of KP, so a
+// thread keeps its k.
+#define FOR_ITEMS(i, v, k)                                                                                              \
+    const int nv = *nv_p;                                                                                               \
+    const int KP = 1 << kshift;                                                                                         \
+    const int k = threadIdx.x & (KP - 1);                                                                               \
+    const int64_t n_items = static_cast<int64_t>(nv) << kshift;                                                         \
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x, v = i >> kshift; i < n_items;         \
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x, v = i >> kshift)
 
-// y0 = b / wbar on occupied cells (:144); np = n*y0 for the first operator application; bb = ||b||^2
-__global__ void __launch_bounds__(256) pcg_init_y_kernel(Grid g, const double* __restrict__ m_cnt, const double* __restrict__ n,
-                                                         const double* __restrict__ wbar, const double* __restrict__ b,
-                                                         double* __restrict__ y, double* __restrict__ np, RhsScalars* sc) {
-    const int k = blockIdx.y;
-    const double* bk = b + k * g.ncell;
+// b_c = compacted b; y0 = b / wbar (:144); np = n * y0; bb = ||b||^2
+__global__ void __launch_bounds__(256) pcg_init_y_kernel(int64_t ncell, const int* __restrict__ nv_p, int kshift, int nrhs, const int* __restrict__ cells,
+                                                         const double* __restrict__ b_dense, const double* __restrict__ n, const double* __restrict__ wbar,
+                                                         double* __restrict__ bc, double* __restrict__ y, double* __restrict__ np, RhsScalars* sc) {
     double bb = 0.0;
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < g.ncell;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const double y0 = m_cnt[j] > 0.0 ? bk[j] / wbar[j] : 0.0;
-        y[k * g.ncell + j] = y0;
-        np[k * g.ncell + j] = n[j] * y0;
-        bb += bk[j] * bk[j];
+    FOR_ITEMS(i, v, k) {
+        if (k < nrhs) {
+            const double bv = b_dense[k * ncell + cells[v]];
+            const double y0 = bv / wbar[v];
+            bc[i] = bv;
+            y[i] = y0;
+            np[i] = n[v] * y0;
+            bb += bv * bv;
+        }
     }
-    block_add2(bb, 0.0, &sc[k].bb, nullptr);
+    block_add_rhs(bb, 0.0, KP, nrhs, sc, 0);
 }
 // r = b - A y0; accumulates rr and rho = r . Minv r
-__global__ void __launch_bounds__(256) pcg_init_r_kernel(Grid g, const double* __restrict__ m, const double* __restrict__ n,
-                                                         const double* __restrict__ wbar, const double* __restrict__ minv,
-                                                         const double* __restrict__ b, const double* __restrict__ y,
-                                                         const double* __restrict__ np, double lam, double* __restrict__ r,
-                                                         RhsScalars* sc) {
-    const int k = blockIdx.y;
-    const int64_t off = k * g.ncell;
+__global__ void __launch_bounds__(256) pcg_init_r_kernel(const int* __restrict__ nv_p, int kshift, int nrhs, const int* __restrict__ nbr,
+                                                         const double* __restrict__ m, const double* __restrict__ n, const double* __restrict__ wbar,
+                                                         const double* __restrict__ minv, const double* __restrict__ bc, const double* __restrict__ y,
+                                                         const double* __restrict__ np, double lam, double* __restrict__ r, RhsScalars* sc) {
     double rr = 0.0, rho = 0.0;
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < g.ncell;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const double blurred = m[j] > 0.0 ? blur_at(g, np + off, j) : 0.0;   // m' > 0 exactly on occupied cells
-        const double ay = lam * (m[j] * y[off + j] - n[j] * blurred) + wbar[j] * y[off + j];
-        const double res = b[off + j] - ay;
-        r[off + j] = res;
-        rr += res * res;
-        rho += res * res * minv[j];
+    FOR_ITEMS(i, v, k) {
+        if (k < nrhs) {
+            const double blurred = blurk(np, nbr + v * 8, i, kshift, k);
+            const double ay = lam * (m[v] * y[i] - n[v] * blurred) + wbar[v] * y[i];
+            const double res = bc[i] - ay;
+            r[i] = res;
+            rr += res * res;
+            rho += res * res * minv[v];
+        }
     }
-    block_add2(rr, rho, &sc[k].rr_next, &sc[k].rho_next);
+    block_add_rhs(rr, rho, KP, nrhs, sc, 1);
 }
 // top of a PCG iteration: convergence test (scipy: ||r|| < rtol*||b||), scalar rotation
 __global__ void pcg_advance_kernel(RhsScalars* sc, int nrhs, double tol_rel, int first) {
@@ -209,60 +334,68 @@ __global__ void pcg_advance_kernel(RhsScalars* sc, int nrhs, double tol_rel, int
     if (sqrt(s.rr) < tol_rel * sqrt(s.bb)) s.done = 1;   // NaN compares false, like scipy
 }
 // p = z + (rho/rho_prev) p with z = Minv r (p = z on the first iteration); np = n * p
-__global__ void __launch_bounds__(256) pcg_direction_kernel(Grid g, const double* __restrict__ n, const double* __restrict__ minv,
-                                                            const double* __restrict__ r, double* __restrict__ p,
+__global__ void __launch_bounds__(256) pcg_direction_kernel(const int* __restrict__ nv_p, int kshift, int nrhs, const double* __restrict__ n,
+                                                            const double* __restrict__ minv, const double* __restrict__ r, double* __restrict__ p,
                                                             double* __restrict__ np, const RhsScalars* sc, int first) {
-    const int k = blockIdx.y;
-    if (sc[k].done) return;
-    const double beta = first ? 0.0 : sc[k].rho / sc[k].rho_prev;
-    const int64_t off = k * g.ncell;
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < g.ncell;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const double z = minv[j] * r[off + j];
-        const double pn = first ? z : z + beta * p[off + j];
-        p[off + j] = pn;
-        np[off + j] = n[j] * pn;
+    const int kk = threadIdx.x & ((1 << kshift) - 1);
+    const bool live = kk < nrhs && !sc[kk].done;
+    const double beta = (live && !first) ? sc[kk].rho / sc[kk].rho_prev : 0.0;
+    FOR_ITEMS(i, v, k) {
+        if (live) {
+            const double z = minv[v] * r[i];
+            const double pn = first ? z : z + beta * p[i];
+            p[i] = pn;
+            np[i] = n[v] * pn;
+        }
     }
 }
 // q = A p; pq += p . q
-__global__ void __launch_bounds__(256) pcg_apply_kernel(Grid g, const double* __restrict__ m, const double* __restrict__ n,
-                                                        const double* __restrict__ wbar, const double* __restrict__ p,
-                                                        const double* __restrict__ np, double lam, double* __restrict__ q,
+__global__ void __launch_bounds__(256) pcg_apply_kernel(const int* __restrict__ nv_p, int kshift, int nrhs, const int* __restrict__ nbr,
+                                                        const double* __restrict__ m, const double* __restrict__ n, const double* __restrict__ wbar,
+                                                        const double* __restrict__ p, const double* __restrict__ np, double lam, double* __restrict__ q,
                                                         RhsScalars* sc) {
-    const int k = blockIdx.y;
-    if (sc[k].done) return;
-    const int64_t off = k * g.ncell;
+    const int kk = threadIdx.x & ((1 << kshift) - 1);
+    const bool live = kk < nrhs && !sc[kk].done;
     double pq = 0.0;
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < g.ncell;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const double blurred = m[j] > 0.0 ? blur_at(g, np + off, j) : 0.0;
-        const double pj = p[off + j];
-        const double qj = lam * (m[j] * pj - n[j] * blurred) + wbar[j] * pj;
-        q[off + j] = qj;
-        pq += pj * qj;
+    FOR_ITEMS(i, v, k) {
+        if (live) {
+            const double blurred = blurk(np, nbr + v * 8, i, kshift, k);
+            const double pj = p[i];
+            const double qj = lam * (m[v] * pj - n[v] * blurred) + wbar[v] * pj;
+            q[i] = qj;
+            pq += pj * qj;
+        }
     }
-    block_add2(pq, 0.0, &sc[k].pq, nullptr);
+    block_add_rhs(pq, 0.0, KP, nrhs, sc, 2);
 }
 // y += alpha p; r -= alpha q; accumulate the next rr / rho
-__global__ void __launch_bounds__(256) pcg_update_kernel(Grid g, const double* __restrict__ minv, const double* __restrict__ p,
-                                                         const double* __restrict__ q, double* __restrict__ y,
+__global__ void __launch_bounds__(256) pcg_update_kernel(const int* __restrict__ nv_p, int kshift, int nrhs, const double* __restrict__ minv,
+                                                         const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ y,
                                                          double* __restrict__ r, RhsScalars* sc) {
-    const int k = blockIdx.y;
-    if (sc[k].done) return;
-    const double alpha = sc[k].rho / sc[k].pq;
-    const int64_t off = k * g.ncell;
+    const int kk = threadIdx.x & ((1 << kshift) - 1);
+    const bool live = kk < nrhs && !sc[kk].done;
+    const double alpha = live ? sc[kk].rho / sc[kk].pq : 0.0;
     double rr = 0.0, rho = 0.0;
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < g.ncell;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        y[off + j] += alpha * p[off + j];
-        const double res = r[off + j] - alpha * q[off + j];
-        r[off + j] = res;
-        rr += res * res;
-        rho += res * res * minv[j];
+    FOR_ITEMS(i, v, k) {
+        if (live) {
+            y[i] += alpha * p[i];
+            const double res = r[i] - alpha * q[i];
+            r[i] = res;
+            rr += res * res;
+            rho += res * res * minv[v];
+        }
     }
-    block_add2(rr, rho, &sc[k].rr_next, &sc[k].rho_next);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sc[k].iters, 1);
+    block_add_rhs(rr, rho, KP, nrhs, sc, 1);
+    if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < nrhs && !sc[threadIdx.x].done) atomicAdd(&sc[threadIdx.x].iters, 1);
 }
+// compact interleaved solution -> the dense (nrhs, ncell) layout the slice stage reads (zero on unoccupied cells)
+__global__ void __launch_bounds__(256) scatter_y_kernel(int64_t ncell, const int* __restrict__ nv_p, int kshift, int nrhs, const int* __restrict__ cells,
+                                                        const double* __restrict__ yc, double* __restrict__ y_dense) {
+    FOR_ITEMS(i, v, k) {
+        if (k < nrhs) y_dense[k * ncell + cells[v]] = yc[i];
+    }
+}
+#undef FOR_ITEMS
 
 // ---- slice + float32 cast + nan_to_num (:153,245) -------------------------------------------------------
 __global__ void __launch_bounds__(256) slice_kernel(Grid g, int z0, int zs, const uint8_t* __restrict__ r,
@@ -321,11 +454,22 @@ extern "C" int64_t vittf_bls_grid_cells(const vittf_bls_params* p) {
     return g.ncell;
 }
 
-// scratch of the grid stage: m, n_a, n_b, minv (ncell each) + r, p, n*p, q (nrhs * ncell each) + scalars
+// scratch of the grid stage, sized for the worst case (every cell occupied; the solve touches the first nv entries only):
+// int32 block sums, vertex count, dense->compact map, compact->dense list, 8 neighbours per vertex; fp64 per-vertex
+// m_cnt, wbar, m', n (x2), Minv; fp64 interleaved [vertex][KP] b, y, r, p, n*p, q; per-rhs scalars
+static int kp_shift(int nrhs) {
+    int s = 0;
+    while ((1 << s) < nrhs) ++s;
+    return s;
+}
 extern "C" int64_t vittf_bls_grid_workspace_bytes(const vittf_bls_params* p, int nrhs) {
     Grid g;
-    if (!p || nrhs <= 0 || make_grid(p, &g) != VITTF_OK) return -1;
-    return 4 * align_up(g.ncell * 8, 256) + 4 * align_up(g.ncell * 8 * nrhs, 256) + align_up(nrhs * sizeof(RhsScalars), 256);
+    if (!p || nrhs <= 0 || nrhs > 64 || make_grid(p, &g) != VITTF_OK) return -1;
+    if (g.ncell >= (1ll << 31)) return -1;
+    const int64_t nblocks = ceil_div_ll(g.ncell, SCAN_BLOCK);
+    const int64_t kp = 1ll << kp_shift(nrhs);
+    return align_up((nblocks + 64) * 4, 256) + 2 * align_up(g.ncell * 4, 256) + align_up(g.ncell * 32, 256) + 6 * align_up(g.ncell * 8, 256) +
+           6 * align_up(g.ncell * 8 * kp, 256) + align_up(nrhs * sizeof(RhsScalars), 256);
 }
 
 extern "C" int64_t vittf_bls_workspace_bytes(const vittf_bls_params* p, int nrhs) {
@@ -388,43 +532,62 @@ extern "C" int vittf_bls_grid_solve(const vittf_bls_params* p, int nrhs, const d
         return VITTF_ERR_NOMEM;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int64_t vec = align_up(g.ncell * 8, 256), per = align_up(g.ncell * 8 * nrhs, 256);
+    const int kshift = kp_shift(nrhs);
+    const int64_t kp = 1ll << kshift;
+    const int64_t nblocks = ceil_div_ll(g.ncell, SCAN_BLOCK);
+    const int64_t vec = align_up(g.ncell * 8, 256), per = align_up(g.ncell * 8 * kp, 256);
     uint8_t* base = static_cast<uint8_t*>(workspace);
     auto take = [&](int64_t bytes) { uint8_t* r = base; base += bytes; return r; };
-    const double* m_cnt = acc;
-    const double* wbar = acc + g.ncell;
-    const double* b = acc + 2 * g.ncell;
+    int* block_sums = reinterpret_cast<int*>(take(align_up((nblocks + 64) * 4, 256)));
+    int* nv = block_sums + nblocks;                      // vertex count, device resident: no host round trip in the solve
+    int* idx_map = reinterpret_cast<int*>(take(align_up(g.ncell * 4, 256)));
+    int* cells = reinterpret_cast<int*>(take(align_up(g.ncell * 4, 256)));
+    int* nbr = reinterpret_cast<int*>(take(align_up(g.ncell * 32, 256)));
+    double* m_cnt_c = reinterpret_cast<double*>(take(vec));
+    double* wbar_c = reinterpret_cast<double*>(take(vec));
     double* m = reinterpret_cast<double*>(take(vec));
     double* n_a = reinterpret_cast<double*>(take(vec));
     double* n_b = reinterpret_cast<double*>(take(vec));
     double* minv = reinterpret_cast<double*>(take(vec));
+    double* bc = reinterpret_cast<double*>(take(per));
+    double* yc = reinterpret_cast<double*>(take(per));
     double* r = reinterpret_cast<double*>(take(per));
     double* pd = reinterpret_cast<double*>(take(per));
     double* np = reinterpret_cast<double*>(take(per));
     double* q = reinterpret_cast<double*>(take(per));
     RhsScalars* sc = reinterpret_cast<RhsScalars*>(take(align_up(nrhs * sizeof(RhsScalars), 256)));
-    const unsigned gc = blocks_for(g.ncell);
+    const double* b = acc + 2 * g.ncell;
     VITTF_CHECK_CUDA(cudaMemsetAsync(sc, 0, nrhs * sizeof(RhsScalars), s));
-    occ_init_kernel<<<gc, 256, 0, s>>>(g.ncell, m_cnt, n_a);
+    VITTF_CHECK_CUDA(cudaMemsetAsync(y, 0, static_cast<size_t>(nrhs) * g.ncell * 8, s));
+    // ---- vertex set: compaction of the occupancy mask (the reference's np.unique, :60-61, without the sort) ----
+    occ_count_kernel<<<static_cast<unsigned>(nblocks), 256, 0, s>>>(g.ncell, acc, block_sums);
+    scan_block_sums_kernel<<<1, 1024, 0, s>>>(block_sums, static_cast<int>(nblocks), nv);
+    compact_kernel<<<static_cast<unsigned>(nblocks), 256, 0, s>>>(g.ncell, acc, block_sums, idx_map, cells);
+    // grids sized for a typical occupancy; every kernel below strides over the device-resident vertex count
+    const unsigned gv = blocks_for(g.ncell / 4 + 1), gk = blocks_for((g.ncell / 4 + 1) * kp);
+    neighbours_kernel<<<gv, 256, 0, s>>>(g, nv, cells, idx_map, acc, nbr, m_cnt_c, wbar_c);
+    // ---- bistochastisation (:107-118) ----
+    fill_ones_kernel<<<gv, 256, 0, s>>>(nv, n_a);
     double* n_cur = n_a;
     double* n_nxt = n_b;
     for (int it = 0; it < 10; ++it) {
-        bistoch_step_kernel<<<gc, 256, 0, s>>>(g, m_cnt, n_cur, n_nxt);
+        bistoch_step_kernel<<<gv, 256, 0, s>>>(nv, nbr, m_cnt_c, n_cur, n_nxt);
         double* tmp = n_cur; n_cur = n_nxt; n_nxt = tmp;
     }
-    bistoch_finish_kernel<<<gc, 256, 0, s>>>(g, m_cnt, n_cur, wbar, p->lam, p->A_diag_min, m, minv);
-    dim3 gk(gc, nrhs);
-    pcg_init_y_kernel<<<gk, 256, 0, s>>>(g, m_cnt, n_cur, wbar, b, y, np, sc);
-    pcg_init_r_kernel<<<gk, 256, 0, s>>>(g, m, n_cur, wbar, minv, b, y, np, p->lam, r, sc);
+    bistoch_finish_kernel<<<gv, 256, 0, s>>>(nv, nbr, n_cur, wbar_c, p->lam, p->A_diag_min, m, minv);
+    // ---- Jacobi-PCG with scipy's stopping rule (:128-154) ----
+    pcg_init_y_kernel<<<gk, 256, 0, s>>>(g.ncell, nv, kshift, nrhs, cells, b, n_cur, wbar_c, bc, yc, np, sc);
+    pcg_init_r_kernel<<<gk, 256, 0, s>>>(nv, kshift, nrhs, nbr, m, n_cur, wbar_c, minv, bc, yc, np, p->lam, r, sc);
     for (int it = 0; it < p->cg_maxiter; ++it) {
         pcg_advance_kernel<<<1, 64, 0, s>>>(sc, nrhs, p->cg_tol, it == 0);
-        pcg_direction_kernel<<<gk, 256, 0, s>>>(g, n_cur, minv, r, pd, np, sc, it == 0);
-        pcg_apply_kernel<<<gk, 256, 0, s>>>(g, m, n_cur, wbar, pd, np, p->lam, q, sc);
-        pcg_update_kernel<<<gk, 256, 0, s>>>(g, minv, pd, q, y, r, sc);
+        pcg_direction_kernel<<<gk, 256, 0, s>>>(nv, kshift, nrhs, n_cur, minv, r, pd, np, sc, it == 0);
+        pcg_apply_kernel<<<gk, 256, 0, s>>>(nv, kshift, nrhs, nbr, m, n_cur, wbar_c, pd, np, p->lam, q, sc);
+        pcg_update_kernel<<<gk, 256, 0, s>>>(nv, kshift, nrhs, minv, pd, q, yc, r, sc);
     }
+    scatter_y_kernel<<<gk, 256, 0, s>>>(g.ncell, nv, kshift, nrhs, cells, yc, y);
     if (iters_out) copy_iters_kernel<<<1, 64, 0, s>>>(sc, nrhs, iters_out);
     VITTF_CHECK_CUDA(cudaGetLastError());
-    vittf_count_launches(10 + 1 + 1 + 2 + 4 * p->cg_maxiter + (iters_out ? 1 : 0));
+    vittf_count_launches(3 + 1 + 1 + 10 + 1 + 2 + 4 * p->cg_maxiter + 1 + (iters_out ? 1 : 0));
     return VITTF_OK;
 }
 
