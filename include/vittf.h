@@ -225,9 +225,10 @@ int vittf_bls_solve(const vittf_bls_params* p, const float* t, const uint8_t* r_
  * Per-voxel arrays are slab-local (.., W, H, z1-z0); r_u8 is always the full (W,H,D) reference.
  *   rank-local : vittf_bls_sobel_slab  -> raw Sobel magnitude of the slab, atomic max into *c_max
  *   exchange   : all-reduce(max) of c_max                       (skipped when a confidence is given)
- *   rank-local : vittf_bls_splat_slab  -> acc += [m | wbar | b_0..b_{nrhs-1}], (2+nrhs)*ncell fp64
+ *   rank-local : vittf_bls_splat_slab  -> acc[cell][m, wbar, b_0..b_{nrhs-1}] +=, ncell*(2+nrhs) fp64, cell-major
  *   exchange   : all-reduce(sum) of acc
- *   replicated : vittf_bls_grid_solve  -> y (nrhs*ncell fp64): bistochastisation + PCG on the grid
+ *   replicated : vittf_bls_grid_solve  -> y (ncell*nrhs fp64, cell-major): vertex compaction, bistochastisation + PCG on the
+ *                                         occupied cells
  *   rank-local : vittf_bls_slice_slab  -> out fp32 slab
  * vittf_bls_solve is exactly this sequence with one slab.                                          */
 int64_t vittf_bls_grid_cells(const vittf_bls_params* p);
