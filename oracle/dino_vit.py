@@ -141,11 +141,72 @@ class VisionTransformer(nn.Module):
         return self.norm(x)[:, 0]
 
 
+# ---------------------------------------------------------------------------------------------
+# DINOv2 (/root/reference/infer.py:45-46: torch.hub.load('facebookresearch/dinov2', 'dinov2_vits14'), patch 14,
+# infer.py:254-260 -- the branch carries a typo (`dinoo_model`, :258) and never ran; this restates the hub model it meant
+# to load from the published dinov2/models/vision_transformer.py: img_size 518 (37 x 37 position grid), LayerScale after
+# the attention and the MLP (init_values 1.0), interpolate_offset 0.1 (the same bicubic rule as DINO v1), no register
+# tokens, mask_token unused at inference.  vitg14 (SwiGLU FFN, 1536-d) is not restated.  Parity: UNPINNED like v1; pin =
+# the parameter count of dinov2_vits14, 22 056 576.
+# ---------------------------------------------------------------------------------------------
+ARCHS_V2 = {
+    "vits14": (384, 12, 6, 14),
+    "vitb14": (768, 12, 12, 14),
+    "vitl14": (1024, 24, 16, 14),
+}
+
+
+class LayerScale(nn.Module):
+    def __init__(self, dim, init_values=1.0):
+        super().__init__()
+        self.gamma = nn.Parameter(init_values * torch.ones(dim))
+
+    def forward(self, x):
+        return x * self.gamma
+
+
+class BlockV2(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio=4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = Attention(dim, num_heads)
+        self.ls1 = LayerScale(dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+        self.ls2 = LayerScale(dim)
+
+    def forward(self, x):
+        x = x + self.ls1(self.attn(self.norm1(x))[0])
+        return x + self.ls2(self.mlp(self.norm2(x)))
+
+
+class DinoV2VisionTransformer(VisionTransformer):
+    def __init__(self, patch_size=14, embed_dim=384, depth=12, num_heads=6, img_size=518):
+        super().__init__(patch_size=patch_size, embed_dim=embed_dim, depth=0, num_heads=num_heads, img_size=img_size)
+        self.blocks = nn.ModuleList([BlockV2(embed_dim, num_heads) for _ in range(depth)])
+        self.mask_token = nn.Parameter(torch.zeros(1, embed_dim))
+        self.blocks.apply(self._init_weights)
+        # LayerScale is 1.0 in the hub constructor and learned afterwards: random values so that a test sees its effect
+        for blk in self.blocks:
+            nn.init.uniform_(blk.ls1.gamma, 0.5, 1.5)
+            nn.init.uniform_(blk.ls2.gamma, 0.5, 1.5)
+
+    def prepare_tokens_with_masks(self, x, masks=None):
+        return self.prepare_tokens(x)
+
+
 def build(name="vits8", seed=0, depth=None):
     """Random-init model under a fixed seed (north_star: random-init weights)."""
-    d, l, h, p = ARCHS[name]
     gen_state = torch.random.get_rng_state()
     torch.manual_seed(seed)
+    if name in ARCHS_V2:
+        d, l, h, p = ARCHS_V2[name]
+        model = DinoV2VisionTransformer(patch_size=p, embed_dim=d, depth=depth or l, num_heads=h).eval()
+        torch.random.set_rng_state(gen_state)
+        for prm in model.parameters():
+            prm.requires_grad_(False)
+        return model
+    d, l, h, p = ARCHS[name]
     model = VisionTransformer(patch_size=p, embed_dim=d, depth=depth or l, num_heads=h).eval()
     torch.random.set_rng_state(gen_state)
     for prm in model.parameters():

@@ -229,3 +229,21 @@ def test_quantized_maps_match_the_reference_expression(shape, z_range):
         z0, z1 = z_range
         out, (zo0, zo1) = ops.quantize_maps_u8(sc[..., z0:z1].contiguous(), cmax, half, depth=shape[2], z0=z0)
         assert (zo0, zo1) == (z0 // 2, z1 // 2) and torch.equal(out.cpu(), ref[..., zo0:zo1])
+
+
+@pytest.mark.parametrize("switch", ["VITTF_SIM_GENERIC", "VITTF_SIM_UP_TC"])
+def test_similarity_kernel_switches(switch):
+    """The two A/B switches of the stage select kernels the default dispatch only uses for part of the shapes:
+    VITTF_SIM_GENERIC = the generic kernels of both passes everywhere, VITTF_SIM_UP_TC = the tcgen05 up-sampling kernel for
+    every prototype count (default: <= 8 prototypes or factor 2).  The NS parity sweep and the configs[0] / configs[1]
+    full-size checks must hold under both (same oracle, same 2e-3)."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    env = dict(os.environ)
+    env[switch] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", str(Path(__file__)), "-x", "-q", "-k",
+                        "ns_similarity_matches_oracle or empty_classes or (full_size and (384-64-128 or 384-64-256))"],
+                       env=env, capture_output=True, text=True, cwd=str(Path(__file__).resolve().parent.parent))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

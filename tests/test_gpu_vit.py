@@ -256,13 +256,15 @@ def test_feature_volume_full_size_properties():
     assert torch.equal(acc, a)
 
 
-@pytest.mark.parametrize("arch,depth", [("vits16", 3), ("vitb16", 2), ("vitb8", 2)])
+@pytest.mark.parametrize("arch,depth", [("vits16", 3), ("vitb16", 2), ("vitb8", 2), ("vits14", 3), ("vitb14", 2), ("vitl14", 2)])
 def test_other_backbones_match_oracle(arch, depth):
     """--dino-model vits16 / vitb16 (patch 16: the 224^2 position grid is 14 x 14 and is always
-    bicubically resampled) and vitb8 (768-d, 12 heads) through the same engine, against the fp32 oracle."""
+    bicubically resampled), vitb8 (768-d, 12 heads) and the DINOv2 backbones --dino2-model vits14 / vitb14 / vitl14
+    (patch 14, 37 x 37 position grid, LayerScale folded into proj / fc2, 1024-d x 16 heads for L) through the same
+    engine, against the fp32 oracle."""
     from oracle import dino_vit, feature_volume as ofv, synth
     from vittf_b200 import infer
-    patch = 16 if arch.endswith("16") else 8
+    patch = int(arch[4:])
     vol, _ = synth.ct_volume((48, 40, 32), n_shells=4, seed=2)
     model = dino_vit.build(arch, seed=1, depth=depth)
     ref = ofv.feature_volume(vol, model, patch=patch, fos=8, batch_size=4)

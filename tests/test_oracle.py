@@ -135,3 +135,25 @@ def test_crop_helpers_match_reference(golden):
 def test_luma_lut_is_not_floor_division():
     lut = bls.luma_lut(5)
     assert (lut != np.arange(256) // 5).sum() == 9
+
+
+def test_dinov2_restatement_pins():
+    """DINOv2 (infer.py:45-46, 254-260): the restated hub model has the published parameter count of dinov2_vits14
+    (22 056 576), the attribute layout the reference hooks, a state dict the product's parameter container loads, and
+    LayerScale acts as a per-channel factor (what the engine folds into proj / fc2)."""
+    import torch
+    from oracle import dino_vit
+    from vittf_b200.dino import build_dino
+    m = dino_vit.build("vits14", seed=0)
+    assert sum(p.numel() for p in m.parameters()) == 22056576
+    assert m._modules["blocks"][-1]._modules["attn"]._modules["qkv"].out_features == 3 * 384 and m.blocks[-1].attn.num_heads == 6
+    w = build_dino("vits14", seed=0)
+    missing, unexpected = w.load_state_dict(m.state_dict(), strict=False)
+    assert not missing and not unexpected
+    blk = dino_vit.build("vits14", seed=1, depth=1).blocks[0]
+    x = torch.randn(2, 5, 384)
+    y, _ = blk.attn(blk.norm1(x))
+    x1 = x + y * blk.ls1.gamma
+    ref = x1 + blk.mlp(blk.norm2(x1)) * blk.ls2.gamma
+    assert torch.allclose(blk(x), ref, atol=1e-6)
+    assert float((blk.ls1.gamma - 1).abs().max()) > 0.05           # random, so that a test sees its effect

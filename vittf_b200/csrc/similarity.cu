@@ -157,314 +157,6 @@ __global__ void __launch_bounds__(128) sim_lowres_kernel(const T* __restrict__ f
 
 
 // ---------------------------------------------------------------------------------------------
-// pass 1, shared-memory tiled (fp16 feature volumes, the cache format of infer.py): one CTA owns a 4 x 8 x 16
-// brick of low-res voxels plus the forward halo its 13 Gram neighbours need; per F-chunk the 5 x 10 x 20 region
-// is staged once in shared memory as half2 words (each thread copies the same two words of every feature plane,
-// addresses computed once) and every thread handles TWO z-adjacent voxels: three 4-byte LDS return the z-values
-// (z-1 .. z+2) of a neighbour row: 15 LDS.32 + A/4 broadcast LDS.128 per feature for 2 x (A + 14) FMAs.
-// ---------------------------------------------------------------------------------------------
-constexpr int TB_X = 4, TB_Y = 8, TB_Z = 16, TCH = 16;
-constexpr int TR_X = TB_X + 1, TR_Y = TB_Y + 2;
-constexpr int TR_W = 10;                        // 4-byte words per staged row: z in [bz0 - 2, bz0 + 18)
-constexpr int TR_WORDS = TR_X * TR_Y * TR_W;    // 500 words per feature
-constexpr int TR_PER_THREAD = (TR_WORDS + 255) / 256;
-
-template <int AT, bool GRAM>
-__global__ void __launch_bounds__(256) sim_lowres_tiled_kernel(const __half* __restrict__ feats, int F, int w, int h, int d,
-                                                               const float* __restrict__ protos, int A, int a_base,
-                                                               float* __restrict__ dots, float* __restrict__ gram) {
-    __shared__ __align__(16) uint32_t s_t[TCH][TR_WORDS];          // half2 words, [rx][ry][word]
-    __shared__ __align__(16) float s_p[TCH][AT];
-    const int64_t n = static_cast<int64_t>(w) * h * d;
-    const int bz0 = blockIdx.x * TB_Z, by0 = blockIdx.y * TB_Y, bx0 = blockIdx.z * TB_X;
-    const int tid = threadIdx.x;
-    const int lx = tid >> 6, ly = (tid >> 3) & 7, lz = (tid & 7) * 2;
-    // staging: every thread owns up to TR_PER_THREAD fixed words of the region (addresses computed once)
-    int64_t ld_off[TR_PER_THREAD];
-    int ld_mode[TR_PER_THREAD];    // 0 skip, 1 zero, 2 aligned half2 load
-#pragma unroll
-    for (int k = 0; k < TR_PER_THREAD; ++k) {
-        const int i = tid + k * 256;
-        ld_mode[k] = 0;
-        ld_off[k] = 0;
-        if (i < TR_WORDS) {
-            const int wd = i % TR_W, ry = (i / TR_W) % TR_Y, rx = i / (TR_W * TR_Y);
-            const int gx = bx0 + rx, gy = by0 + ry - 1, gz = bz0 - 2 + wd * 2;     // even: d is even, word never straddles
-            const bool ok = gx < w && gy >= 0 && gy < h && gz >= 0 && gz < d;
-            ld_mode[k] = ok ? 2 : 1;
-            ld_off[k] = ok ? (static_cast<int64_t>(gx) * h + gy) * d + gz : 0;
-        }
-    }
-    float acc[2][AT];
-    float g[2][14];
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-#pragma unroll
-        for (int i = 0; i < AT; ++i) acc[v][i] = 0.0f;
-#pragma unroll
-        for (int o = 0; o < 14; ++o) g[v][o] = 0.0f;
-    }
-    for (int f0 = 0; f0 < F; f0 += TCH) {
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < TR_PER_THREAD; ++k) {
-            if (ld_mode[k] == 0) continue;
-#pragma unroll 4
-            for (int ff = 0; ff < TCH; ++ff) {
-                uint32_t v = 0;
-                if (ld_mode[k] == 2 && f0 + ff < F)
-                    v = __ldg(reinterpret_cast<const uint32_t*>(feats + static_cast<int64_t>(f0 + ff) * n + ld_off[k]));
-                s_t[ff][tid + k * 256] = v;
-            }
-        }
-        for (int i = tid; i < TCH * AT; i += 256) {
-            const int ff = i / AT, aa = i - ff * AT;
-            s_p[ff][aa] = (a_base + aa < A && f0 + ff < F) ? protos[static_cast<int64_t>(a_base + aa) * F + f0 + ff] : 0.0f;
-        }
-        __syncthreads();
-#pragma unroll 2
-        for (int ff = 0; ff < TCH; ++ff) {
-            // rows: 0 (x,y)  1 (x,y+1)  2 (x+1,y-1)  3 (x+1,y)  4 (x+1,y+1); values z-1 .. z+2 of voxel pair (z, z+1)
-            float r[5][4];
-            const int rxs[5] = {lx, lx, lx + 1, lx + 1, lx + 1};
-            const int rys[5] = {ly + 1, ly + 2, ly, ly + 1, ly + 2};
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                // words cover z-2..z-1 | z..z+1 | z+2..z+3 (word index lz/2 .. lz/2+2)
-                const uint32_t* pr = &s_t[ff][(rxs[k] * TR_Y + rys[k]) * TR_W + (lz >> 1)];
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(pr));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(pr + 1));
-                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(pr + 2));
-                r[k][0] = a.y; r[k][1] = b.x; r[k][2] = b.y; r[k][3] = c.x;
-            }
-#pragma unroll
-            for (int i = 0; i < AT; i += 4) {
-                const float4 pv = *reinterpret_cast<const float4*>(&s_p[ff][i]);
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    const float c = r[0][1 + v];
-                    acc[v][i + 0] = fmaf(c, pv.x, acc[v][i + 0]);
-                    acc[v][i + 1] = fmaf(c, pv.y, acc[v][i + 1]);
-                    acc[v][i + 2] = fmaf(c, pv.z, acc[v][i + 2]);
-                    acc[v][i + 3] = fmaf(c, pv.w, acc[v][i + 3]);
-                }
-            }
-            if (GRAM) {
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    const float c = r[0][1 + v];
-                    g[v][0] = fmaf(c, c, g[v][0]);
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                        for (int dz = -1; dz <= 1; ++dz)
-                            g[v][1 + (dy + 1) * 3 + (dz + 1)] = fmaf(c, r[3 + dy][1 + v + dz], g[v][1 + (dy + 1) * 3 + (dz + 1)]);
-#pragma unroll
-                    for (int dz = -1; dz <= 1; ++dz) g[v][11 + dz] = fmaf(c, r[1][1 + v + dz], g[v][11 + dz]);
-                    g[v][13] = fmaf(c, r[0][2 + v], g[v][13]);
-                }
-            }
-        }
-    }
-    const int gx = bx0 + lx, gy = by0 + ly;
-    if (gx >= w || gy >= h) return;
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-        const int gz = bz0 + lz + v;
-        if (gz >= d) continue;
-        const int64_t vox = (static_cast<int64_t>(gx) * h + gy) * d + gz;
-#pragma unroll
-        for (int i = 0; i < AT; ++i)
-            if (a_base + i < A) dots[static_cast<int64_t>(a_base + i) * n + vox] = acc[v][i];
-        if (GRAM) {
-#pragma unroll
-            for (int o = 0; o < 14; ++o) gram[static_cast<int64_t>(o) * n + vox] = g[v][o];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// pass 1, TMA-fed (fp16 feature volumes with d % 8 == 0): one CTA of 128 threads owns a 4 x 8 x 16 brick of low-res
-// voxels; the 5 x 10 x 32 halo region of LF_FS feature planes arrives per stage as ONE 4-D tensor-map box
-// (cp.async.bulk.tensor, out-of-volume coordinates zero-filled -- exactly the "no neighbour" Gram convention), three
-// stages deep (six for the halo-free boxes of the dots-only launches), so loads overlap the arithmetic.  Every thread owns FOUR z-adjacent voxels: per feature 5 rows x
-// (LDS.64 + LDS.32) give z-1 .. z+4 of every neighbour row for 4 x 14 Gram FMAs, and the prototype dots run as packed
-// FFMA2 (two prototypes per instruction) against a prototype panel that stays in shared memory for the whole kernel.
-// ---------------------------------------------------------------------------------------------
-constexpr int LF_BX = 4, LF_BY = 8, LF_BZ = 16, LF_FS = 8;
-template <bool GRAM> constexpr int lf_stages() { return GRAM ? 2 : 4; }   // deep enough to cover the TMA latency
-constexpr int LF_RX = LF_BX + 1, LF_RY = LF_BY + 2, LF_RZ = 40;          // region: z in [bz0 - 8, bz0 + 32) (80-byte rows: 20-word pitch spreads the rows over the banks) -- the box start
-                                                                          // must be 16-byte aligned in global memory (tools/ubench/tma4d.cu)
-constexpr int LF_STAGE_BYTES = LF_FS * LF_RX * LF_RY * LF_RZ * 2;         // 25600
-
-template <int AT, bool GRAM>
-__global__ void __launch_bounds__(128) sim_lowres_tma_kernel(const __grid_constant__ CUtensorMap tm_f, int F, int w, int h, int d,
-                                                             const float* __restrict__ protos, int A, int a_base,
-                                                             float* __restrict__ dots, float* __restrict__ gram) {
-    extern __shared__ __align__(128) uint8_t lf_smem[];
-    uint8_t* s_t = lf_smem;                                              // [stage][f][rx][ry][24] halves
-    float* s_p = reinterpret_cast<float*>(lf_smem + lf_stages<GRAM>() * (GRAM ? LF_STAGE_BYTES : LF_FS * LF_BX * LF_BY * LF_BZ * 2));   // [F][AT]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_p + static_cast<size_t>(F) * AT);
-    const int tid = threadIdx.x;
-    const int bz0 = blockIdx.x * LF_BZ, by0 = blockIdx.y * LF_BY, bx0 = blockIdx.z * LF_BX;
-    const int lx = tid >> 5, ly = (tid >> 2) & 7, lz = (tid & 3) * 4;
-    constexpr int LF_STAGES = lf_stages<GRAM>();
-    const int nchunk = (F + LF_FS - 1) / LF_FS;
-    // without the Gram planes no halo is needed: the box is the brick itself (RX x RY x RZ = 4 x 8 x 16)
-    constexpr int RX = GRAM ? LF_RX : LF_BX, RY = GRAM ? LF_RY : LF_BY, RZ = GRAM ? LF_RZ : LF_BZ;
-    constexpr int STAGE_BYTES = LF_FS * RX * RY * RZ * 2;
-    if (tid == 0) {
-        for (int i = 0; i < LF_STAGES; ++i) ptx::mbar_init(&full[i], 1);
-        ptx::fence_barrier_init();
-    }
-    __syncthreads();
-    auto issue = [&](int c) {
-        uint64_t* bar = &full[c % LF_STAGES];
-        ptx::mbar_arrive_expect_tx(bar, STAGE_BYTES);
-        ptx::tma_load_4d(s_t + (c % LF_STAGES) * STAGE_BYTES, &tm_f, bar, GRAM ? bz0 - 8 : bz0, GRAM ? by0 - 1 : by0, bx0, c * LF_FS);
-    };
-    if (tid == 0) {
-        ptx::prefetch_tmap(&tm_f);
-        for (int c = 0; c < LF_STAGES && c < nchunk; ++c) issue(c);
-    }
-    // prototype panel, transposed to [f][a]: coalesced 16-byte loads along f, all in flight at once
-    if constexpr (AT == 0) {
-        // Gram planes only (the dots run on the tensor cores, sim_dots_mma_kernel)
-    } else if ((F & 3) == 0 && (reinterpret_cast<uintptr_t>(protos) & 15) == 0) {
-        const int f4n = F >> 2;
-#pragma unroll 4
-        for (int i = tid; i < f4n * AT; i += 128) {
-            const int aa = i / f4n, f4 = i - aa * f4n;
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (a_base + aa < A) v = __ldg(reinterpret_cast<const float4*>(protos + static_cast<size_t>(a_base + aa) * F) + f4);
-            float* dstp = s_p + static_cast<size_t>(4 * f4) * AT + aa;
-            dstp[0] = v.x; dstp[AT] = v.y; dstp[2 * AT] = v.z; dstp[3 * AT] = v.w;
-        }
-    } else {
-        for (int i = tid; i < F * AT; i += 128) {
-            const int ff = i / AT, aa = i - ff * AT;
-            s_p[i] = a_base + aa < A ? protos[static_cast<size_t>(a_base + aa) * F + ff] : 0.0f;
-        }
-    }
-    __syncthreads();
-
-    constexpr int AH = AT > 0 ? AT / 2 : 1;
-    ptx::F2 acc[4][AH];
-    float g[4][14];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-#pragma unroll
-        for (int i = 0; i < AH; ++i) acc[v][i].v = 0ull;
-#pragma unroll
-        for (int o = 0; o < 14; ++o) g[v][o] = 0.0f;
-    }
-    // byte offsets of the five neighbour rows inside one feature plane of a stage; the word at the offset holds
-    // (z-2, z-1), the next two words z .. z+3, the fourth (z+4, z+5)
-    constexpr int ROWB = RZ * 2;
-    const int zo = GRAM ? (6 + lz) * 2 : lz * 2 - 4;          // without halo: "word 1" is the start of the run
-    const int yo = GRAM ? 1 : 0;
-    const int row_off[5] = {((lx * RY) + ly + yo) * ROWB + zo, ((lx * RY) + ly + 2) * ROWB + zo,
-                            (((lx + 1) * RY) + ly) * ROWB + zo, (((lx + 1) * RY) + ly + 1) * ROWB + zo,
-                            (((lx + 1) * RY) + ly + 2) * ROWB + zo};
-    for (int c = 0; c < nchunk; ++c) {
-        ptx::mbar_wait(&full[c % LF_STAGES], (c / LF_STAGES) & 1);
-        const uint8_t* st = s_t + (c % LF_STAGES) * STAGE_BYTES;
-        const int fmax = min(LF_FS, F - c * LF_FS);
-#pragma unroll 2
-        for (int ff = 0; ff < fmax; ++ff) {
-            const uint8_t* pl = st + ff * (RX * RY * ROWB);
-            float r[GRAM ? 5 : 1][6];
-#pragma unroll
-            for (int k = 0; k < (GRAM ? 5 : 1); ++k) {
-                const uint32_t w0 = GRAM ? *reinterpret_cast<const uint32_t*>(pl + row_off[k]) : 0u;
-                const uint2 w12 = *reinterpret_cast<const uint2*>(pl + row_off[k] + 4);
-                const uint32_t w3 = GRAM ? *reinterpret_cast<const uint32_t*>(pl + row_off[k] + 12) : 0u;
-                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&w12.x));
-                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w12.y));
-                r[k][0] = __half2float(__ushort_as_half(static_cast<unsigned short>(w0 >> 16)));
-                r[k][1] = f1.x; r[k][2] = f1.y; r[k][3] = f2.x; r[k][4] = f2.y;
-                r[k][5] = __half2float(__ushort_as_half(static_cast<unsigned short>(w3 & 0xffffu)));
-            }
-            const float* pf = s_p + static_cast<size_t>(c * LF_FS + ff) * AT;
-#pragma unroll
-            for (int i = 0; i < AT / 2; i += 2) {       // (no iterations when AT == 0)
-                const float4 pv = *reinterpret_cast<const float4*>(pf + 2 * i);     // broadcast: same address in every lane
-                const ptx::F2 p01 = ptx::f2_make(pv.x, pv.y), p23 = ptx::f2_make(pv.z, pv.w);
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const ptx::F2 cc = ptx::f2_make(r[0][v + 1], r[0][v + 1]);
-                    acc[v][i] = ptx::f2_fma(p01, cc, acc[v][i]);
-                    acc[v][i + 1] = ptx::f2_fma(p23, cc, acc[v][i + 1]);
-                }
-            }
-            if (GRAM) {
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const float cv = r[0][v + 1];
-                    g[v][0] = fmaf(cv, cv, g[v][0]);
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                        for (int dz = -1; dz <= 1; ++dz)
-                            g[v][1 + (dy + 1) * 3 + (dz + 1)] = fmaf(cv, r[GRAM ? 3 + dy : 0][v + 1 + dz], g[v][1 + (dy + 1) * 3 + (dz + 1)]);
-#pragma unroll
-                    for (int dz = -1; dz <= 1; ++dz) g[v][11 + dz] = fmaf(cv, r[GRAM ? 1 : 0][v + 1 + dz], g[v][11 + dz]);
-                    g[v][13] = fmaf(cv, r[0][v + 2], g[v][13]);
-                }
-            }
-        }
-        __syncthreads();                                   // every thread is done with this stage
-        if (tid == 0 && c + LF_STAGES < nchunk) issue(c + LF_STAGES);
-    }
-    const int gx = bx0 + lx, gy = by0 + ly, gz = bz0 + lz;
-    if (gx >= w || gy >= h || gz >= d) return;
-    const size_t n = static_cast<size_t>(w) * h * d;
-    const size_t vox = (static_cast<size_t>(gx) * h + gy) * d + gz;
-    const bool vec = gz + 4 <= d && (d & 3) == 0;
-#pragma unroll
-    for (int i = 0; i < AT; ++i) {
-        if (a_base + i >= A) break;
-        float o[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            float lo, hi;
-            ptx::f2_get(acc[v][i >> 1], lo, hi);
-            o[v] = (i & 1) ? hi : lo;
-        }
-        float* dst = dots + static_cast<size_t>(a_base + i) * n + vox;
-        if (vec) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-        else
-            for (int v = 0; v < 4 && gz + v < d; ++v) dst[v] = o[v];
-    }
-    if (GRAM) {
-#pragma unroll
-        for (int o = 0; o < 14; ++o) {
-            float* dst = gram + static_cast<size_t>(o) * n + vox;
-            if (vec) *reinterpret_cast<float4*>(dst) = make_float4(g[0][o], g[1][o], g[2][o], g[3][o]);
-            else
-                for (int v = 0; v < 4 && gz + v < d; ++v) dst[v] = g[v][o];
-        }
-    }
-}
-
-template <int AT, bool GRAM>
-int launch_lowres_tma_one(const CUtensorMap& tm, int F, int w, int h, int d, const float* protos, int A, int a_base,
-                          float* dots, float* gram, cudaStream_t s) {
-    const size_t stage = GRAM ? LF_STAGE_BYTES : LF_FS * LF_BX * LF_BY * LF_BZ * 2;
-    const size_t smem = static_cast<size_t>(lf_stages<GRAM>()) * stage + static_cast<size_t>(F) * AT * 4 + 64;
-    auto kern = sim_lowres_tma_kernel<AT, GRAM>;
-    static PerDeviceMemo configured;
-    if (smem > configured.cur()) {
-        VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured.cur() = smem;
-    }
-    dim3 grid(ceil_div(d, LF_BZ), ceil_div(h, LF_BY), ceil_div(w, LF_BX));
-    kern<<<grid, 128, smem, s>>>(tm, F, w, h, d, protos, A, a_base, dots, gram);
-    vittf_count_launches(1);
-    return VITTF_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
 // pass 1, prototype dots on the tensor cores (fp16 feature volumes): dots[a][v] = sum_f feats[f][v] * protos[a][f] is a
 // (n_lr x F) x (F x A) GEMM whose A operand is stored "voxel-major" -- exactly what ldmatrix.trans delivers.  Warp-level
 // mma.sync (m16n8k16, fp32 accumulate) is ample here: the kernel only has to keep up with the feature stream from HBM
@@ -871,61 +563,6 @@ int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const flo
     return VITTF_OK;
 }
 
-// The Gram planes ride along with the first group of <= 16 prototypes (halo box); the remaining prototypes run in
-// groups of <= 32 on halo-free boxes.
-template <bool GRAM>
-int launch_lowres_tma(const __half* feats, int F, int w, int h, int d, const float* protos, int A, float* dots, float* gram,
-                      cudaStream_t s, int layout = 0) {
-    CUtensorMap tm_halo, tm_brick;
-    const uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(h), static_cast<uint64_t>(w), static_cast<uint64_t>(F)};
-    const uint64_t strides[3] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(h) * d * 2, static_cast<uint64_t>(w) * h * d * 2};
-    const uint32_t box_halo[4] = {LF_RZ, LF_RY, LF_RX, LF_FS}, box_brick[4] = {LF_BZ, LF_BY, LF_BX, LF_FS};
-    VITTF_CHECK(vittf_make_tmap(&tm_halo, feats, 2, 4, dims, strides, box_halo, false));
-    VITTF_CHECK(vittf_make_tmap(&tm_brick, feats, 2, 4, dims, strides, box_brick, false));
-    int a_base = 0;
-    const int64_t n = static_cast<int64_t>(w) * h * d;
-    static const bool no_mma = getenv("VITTF_SIM_NO_MMA") != nullptr;     // A/B switch: FFMA2 dots
-    static const bool no_fused = getenv("VITTF_SIM_NO_FUSED") != nullptr; // A/B switch: dots (tensor cores) + Gram (FMA pipe) as two kernels
-    if (!no_mma && !no_fused && F % DM_BK == 0 && d % 8 == 0) {
-        const int rc = launch_lowres_mma(feats, F, w, h, d, protos, A, dots, GRAM ? gram : nullptr, s, layout);
-        if (rc != -1) return rc;
-    }
-    VITTF_REQUIRE(layout == 0, "vittf_sim_lowres: the voxel-major dots layout needs the fused tensor-core pass (fp16 features, F %% 32 == 0, d %% 8 == 0)");
-    if (!no_mma && F % DM_BK == 0 && n % 8 == 0) {
-        // dots of all prototypes on the tensor cores; the Gram planes (the only part that needs the halo) on the FMA pipe
-        VITTF_CHECK(launch_dots_mma(feats, F, n, protos, A, dots, s));
-        if (GRAM) {
-            const int rc = launch_lowres_tma_one<0, true>(tm_halo, F, w, h, d, protos, A, 0, dots, gram, s);
-            VITTF_CHECK(rc);
-        }
-        VITTF_CHECK_CUDA(cudaGetLastError());
-        return VITTF_OK;
-    }
-    if (GRAM) {
-        const int rc = A > 8 ? launch_lowres_tma_one<16, true>(tm_halo, F, w, h, d, protos, A, 0, dots, gram, s)
-                             : launch_lowres_tma_one<8, true>(tm_halo, F, w, h, d, protos, A, 0, dots, gram, s);
-        VITTF_CHECK(rc);
-        a_base = A > 8 ? 16 : 8;
-    }
-    while (a_base < A) {
-        const int rem = A - a_base;
-        int rc;
-        if (rem > 16 && static_cast<size_t>(F) * 32 * 4 <= 96 * 1024) {
-            rc = launch_lowres_tma_one<32, false>(tm_brick, F, w, h, d, protos, A, a_base, dots, gram, s);
-            a_base += 32;
-        } else if (rem > 8) {
-            rc = launch_lowres_tma_one<16, false>(tm_brick, F, w, h, d, protos, A, a_base, dots, gram, s);
-            a_base += 16;
-        } else {
-            rc = launch_lowres_tma_one<8, false>(tm_brick, F, w, h, d, protos, A, a_base, dots, gram, s);
-            a_base += 8;
-        }
-        VITTF_CHECK(rc);
-    }
-    VITTF_CHECK_CUDA(cudaGetLastError());
-    return VITTF_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
 // pass 2: per output voxel.  Index rule of F.interpolate(mode='trilinear', align_corners=False):
 //   src = max((dst + 0.5) * in/out - 0.5, 0); i0 = floor(src); i1 = min(i0 + 1, in - 1); t = src - i0.
@@ -1021,225 +658,6 @@ __global__ void __launch_bounds__(256) sim_upsample_kernel(UpParams q) {
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// pass 2, fast path for integer up-sampling factors U in {2, 4, 8} (the benchmark shapes: 64^3 -> 256^3,
-// 128^3 -> 512^3, 64^3 -> 512^3).  With align_corners=False every low-res CELL c in [-1, n-1] owns the U
-// outputs o = U*c + U/2 + k, k in [0, U), whose weights t_k = (k + 0.5) / U do not depend on c.  One thread
-// owns (cell, kx, group of 4 ky) and produces a 4 x U block of outputs (U contiguous floats along z):
-//   * the 8 corner dots of a prototype are loaded once and interpolated SEPARABLY (x, then z, then y):
-//     1.75 lerps per output voxel and prototype instead of 8 FMAs;
-//   * |interp(f)|^2 = w^T G w is contracted separably from the 36 Gram scalars of the cell (~7 FMA / voxel);
-//   * lanes run along z, so a warp writes 32 * U contiguous floats per output row.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float inv_norm_of(float n2) { return rsqrtf(fmaxf(n2, 1e-24f)); }   // 1 / max(|v|, 1e-12)
-
-template <int U>
-__global__ void __launch_bounds__(32 * U * (U / 4 > 0 ? U / 4 : 1))
-    sim_upsample_cells_kernel(UpParams q) {
-    constexpr int KY = U < 4 ? U : 4;          // output rows (y) per thread
-    extern __shared__ int s_off[];
-    for (int i = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); i <= q.C;
-         i += blockDim.x * blockDim.y * blockDim.z)
-        s_off[i] = q.class_offsets[i];
-    __syncthreads();
-    const int n = q.w;                          // cubic low-res grid, n % 32 == 0 (checked by the host)
-    // lanes run over the n cells cz = 0 .. n-1 (no idle lanes); the half cell cz = -1 (outputs 0 .. U/2-1, both z
-    // corners clamp to z = 0) is produced by the lane that owns cz = 0, from the corner values it holds anyway
-    const int cz = static_cast<int>(blockIdx.x * 32 + threadIdx.x);
-    const int cy = static_cast<int>(blockIdx.y) - 1, cx = static_cast<int>(blockIdx.z) - 1;
-    const int kx = threadIdx.y, ky0 = threadIdx.z * KY;
-    const bool edge_blk = blockIdx.x == 0 && q.z0 < U / 2;   // warp-uniform: this CTA also evaluates the cz = -1 half cell
-    const int ox = U * cx + U / 2 + kx;
-    if (ox < 0 || ox >= q.W) return;
-    const int oy_base = U * cy + U / 2 + ky0, oz_base = U * cz + U / 2;
-    const int zs = q.z1 - q.z0;
-    const bool edge_lane = edge_blk && cz == 0;
-    // warp-uniform: the warp's 32 cells lie inside the z-slab and output rows start 16-byte aligned
-    const int wz_lo = U * static_cast<int>(blockIdx.x * 32), wz_hi = wz_lo + 32 * U + U / 2;
-    const bool fast_store = wz_lo >= q.z0 && (wz_hi <= q.z1 || (static_cast<int>(blockIdx.x) * 32 + 32 == n && q.z1 == q.D)) && q.z0 % 4 == 0 && zs % 4 == 0 &&
-                            (reinterpret_cast<uintptr_t>(q.out) & 15) == 0;
-    if ((oz_base + U <= q.z0 || oz_base >= q.z1) && !edge_blk) return;
-    const int x0 = cx < 0 ? 0 : cx, x1 = cx + 1 > n - 1 ? n - 1 : cx + 1;
-    const int y0 = cy < 0 ? 0 : cy, y1 = cy + 1 > n - 1 ? n - 1 : cy + 1;
-    const int z0 = cz, z1 = cz + 1 > n - 1 ? n - 1 : cz + 1;
-    const float tx = (kx + 0.5f) / U;
-    const uint32_t n_lr = static_cast<uint32_t>(n) * n * n;
-    uint32_t idx[8];                            // 32-bit element offsets inside one (n^3) plane
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        idx[c] = (static_cast<uint32_t>((c >> 2) ? x1 : x0) * n + (((c >> 1) & 1) ? y1 : y0)) * n + ((c & 1) ? z1 : z0);
-    float tys[KY], tzs[U];
-#pragma unroll
-    for (int ky = 0; ky < KY; ++ky) tys[ky] = (ky0 + ky + 0.5f) / U;
-#pragma unroll
-    for (int kz = 0; kz < U; ++kz) tzs[kz] = (kz + 0.5f) / U;
-
-    // ---- 1 / |interp(f)| for the KY x U outputs (+ KY outputs of the z edge) --------------------------------
-    float inv[KY][U], inv_e[KY];
-    if (q.mode == VITTF_SIM_NS) {
-        // corner Gram matrix (symmetric 8 x 8) from the 14 forward-neighbour planes
-        const int cxs[2] = {x0, x1}, cys[2] = {y0, y1}, czs[2] = {z0, z1};
-        float G[8][8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-#pragma unroll
-            for (int b = a; b < 8; ++b) {
-                bool swap;
-                const int slot = gram_slot(cxs[b >> 2] - cxs[a >> 2], cys[(b >> 1) & 1] - cys[(a >> 1) & 1],
-                                           czs[b & 1] - czs[a & 1], swap);
-                const float g = __ldg(q.gram + static_cast<size_t>(slot) * n_lr + (swap ? idx[b] : idx[a]));
-                G[a][b] = g;
-                G[b][a] = g;
-            }
-        // contract x (fixed tx): H[(y,z)][(y',z')] = sum_{x,x'} wx wx' G[(x,y,z)][(x',y',z')]
-        const float wx[2] = {1.0f - tx, tx};
-        float H[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = a; b < 4; ++b) {
-                const float v = wx[0] * wx[0] * G[a][b] + wx[0] * wx[1] * (G[a][4 + b] + G[4 + a][b]) + wx[1] * wx[1] * G[4 + a][4 + b];
-                H[a][b] = v;
-                H[b][a] = v;
-            }
-#pragma unroll
-        for (int kz = 0; kz < U; ++kz) {
-            const float wz[2] = {1.0f - tzs[kz], tzs[kz]};
-            // contract z: J[y][y'] ; index of (y,z) in H is y*2+z
-            float J[2][2];
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = a; b < 2; ++b) {
-                    const float v = wz[0] * wz[0] * H[a * 2][b * 2] + wz[0] * wz[1] * (H[a * 2][b * 2 + 1] + H[a * 2 + 1][b * 2]) +
-                                    wz[1] * wz[1] * H[a * 2 + 1][b * 2 + 1];
-                    J[a][b] = v;
-                    J[b][a] = v;
-                }
-#pragma unroll
-            for (int ky = 0; ky < KY; ++ky) {
-                const float ty = tys[ky];
-                inv[ky][kz] = inv_norm_of((1.0f - ty) * (1.0f - ty) * J[0][0] + 2.0f * ty * (1.0f - ty) * J[0][1] + ty * ty * J[1][1]);
-            }
-        }
-#pragma unroll
-        for (int ky = 0; ky < KY; ++ky) {      // z edge: both z corners are z0
-            const float ty = tys[ky];
-            inv_e[ky] = inv_norm_of((1.0f - ty) * (1.0f - ty) * H[0][0] + 2.0f * ty * (1.0f - ty) * H[0][2] + ty * ty * H[2][2]);
-        }
-    } else {
-#pragma unroll
-        for (int ky = 0; ky < KY; ++ky) {
-            inv_e[ky] = 1.0f;
-#pragma unroll
-            for (int kz = 0; kz < U; ++kz) inv[ky][kz] = 1.0f;
-        }
-    }
-
-    // ---- per class: max over its prototypes of the separably interpolated dots --------------------------
-    const size_t plane = static_cast<size_t>(q.H) * zs;
-    const size_t n_out = static_cast<size_t>(q.W) * plane;
-    for (int c = 0; c < q.C; ++c) {
-        float best[KY][U], best_e[KY];
-#pragma unroll
-        for (int ky = 0; ky < KY; ++ky) {
-            best_e[ky] = -INFINITY;
-#pragma unroll
-            for (int kz = 0; kz < U; ++kz) best[ky][kz] = -INFINITY;
-        }
-        const int a_end = s_off[c + 1];
-        const float* da = q.dots + static_cast<size_t>(s_off[c]) * n_lr;   // uniform base, 32-bit per-thread offsets
-        for (int a = s_off[c]; a < a_end; ++a, da += n_lr) {
-            float v[4];                                  // x-interpolated corners, index y*2+z
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float lo = __ldg(da + idx[k]), hi = __ldg(da + idx[4 + k]);
-                v[k] = fmaf(tx, hi - lo, lo);
-            }
-            const float dz0 = v[1] - v[0], dz1 = v[3] - v[2];
-#pragma unroll
-            for (int kz = 0; kz < U; ++kz) {
-                const float r0 = fmaf(tzs[kz], dz0, v[0]);       // y0 row
-                const float r1 = fmaf(tzs[kz], dz1, v[2]);       // y1 row
-                const float dr = r1 - r0;
-#pragma unroll
-                for (int ky = 0; ky < KY; ++ky) best[ky][kz] = fmaxf(best[ky][kz], fmaf(tys[ky], dr, r0));
-            }
-            if (edge_blk) {
-                const float dr = v[2] - v[0];
-#pragma unroll
-                for (int ky = 0; ky < KY; ++ky) best_e[ky] = fmaxf(best_e[ky], fmaf(tys[ky], dr, v[0]));
-            }
-        }
-        float* oc = q.out + static_cast<size_t>(c) * n_out + static_cast<size_t>(ox) * plane;
-        // clamp(0,1)**e with the exponent dispatched once per class (uniform), not once per voxel
-        auto finish = [&](auto kind) {
-            constexpr int K = decltype(kind)::value;
-            auto tr = [&](float sim) {
-                const float x = fminf(fmaxf(sim, 0.0f), 1.0f);
-                if (K == 0) return x * x;
-                if (K == 1) return x * x * sqrtf(x);
-                if (K == 2) return x;
-                return x > 0.0f ? __powf(x, q.exponent) : 0.0f;
-            };
-#pragma unroll
-            for (int ky = 0; ky < KY; ++ky) {
-                const int oy = oy_base + ky;
-                float r[U];
-#pragma unroll
-                for (int kz = 0; kz < U; ++kz) r[kz] = tr(best[ky][kz] * inv[ky][kz]);
-                float* row = oc + static_cast<size_t>(oy) * zs;
-                if (U == 4 && fast_store) {
-                    // lanes hold outputs [4cz+2, 4cz+6): pull the upper half of the lower neighbour so that every lane
-                    // writes the ALIGNED float4 [4cz, 4cz+4) -- a warp then stores 512 contiguous bytes per row
-                    const float p2 = __shfl_up_sync(0xffffffffu, r[2], 1), p3 = __shfl_up_sync(0xffffffffu, r[3], 1);
-                    if (oy >= 0 && oy < q.H) {
-                        float* dst = row + (4 * cz - q.z0);
-                        if (threadIdx.x > 0) *reinterpret_cast<float4*>(dst) = make_float4(p2, p3, r[0], r[1]);
-                        else *reinterpret_cast<float2*>(dst + 2) = make_float2(r[0], r[1]);
-                        if (threadIdx.x == 31) {     // upper half of the warp's last cell; the last cell of the grid has none
-                            if (cz < n - 1) *reinterpret_cast<float2*>(dst + 4) = make_float2(r[2], r[3]);
-                        }
-                    }
-                } else if (U == 8 && fast_store) {
-                    // oz_base = 8 cz + 4: both halves of the lane's 8 outputs are 16-byte aligned
-                    if (oy >= 0 && oy < q.H && cz < n - 1) {
-                        float* dst = row + (oz_base - q.z0);
-                        *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
-                        *reinterpret_cast<float4*>(dst + 4) = make_float4(r[4], r[5], r[6], r[7]);
-                    } else if (oy >= 0 && oy < q.H) {
-                        *reinterpret_cast<float4*>(row + (oz_base - q.z0)) = make_float4(r[0], r[1], r[2], r[3]);
-                    }
-                } else if (oy >= 0 && oy < q.H) {
-                    float* dst = row + (oz_base - q.z0);
-#pragma unroll
-                    for (int kz = 0; kz < U; ++kz) {
-                        const int oz = oz_base + kz;
-                        if (oz >= q.z0 && oz < q.z1 && oz < q.D) dst[kz] = r[kz];
-                    }
-                }
-                if (edge_lane && oy >= 0 && oy < q.H) {
-                    const float re = tr(best_e[ky] * inv_e[ky]);
-#pragma unroll
-                    for (int oz = 0; oz < U / 2; ++oz)
-                        if (oz >= q.z0 && oz < q.z1) row[oz - q.z0] = re;
-                }
-            }
-        };
-        if (q.exponent == 2.0f) finish(std::integral_constant<int, 0>{});
-        else if (q.exponent == 2.5f) finish(std::integral_constant<int, 1>{});
-        else if (q.exponent == 1.0f) finish(std::integral_constant<int, 2>{});
-        else finish(std::integral_constant<int, 3>{});
-    }
-}
-
-template <int U>
-void launch_cells(const UpParams& q, cudaStream_t s) {
-    constexpr int KY = U < 4 ? U : 4;
-    dim3 block(32, U, U / KY);
-    dim3 grid(q.w / 32, q.w + 1, q.w + 1);
-    sim_upsample_cells_kernel<U><<<grid, block, (q.C + 1) * sizeof(int), s>>>(q);
-}
 
 // ---------------------------------------------------------------------------------------------
 // pass 2 on the tensor cores (NS mode, U in {4, 8}).  Inside a low-res cell the U^3 outputs of one prototype are
@@ -1621,222 +1039,6 @@ int launch_upsample_mma(const UpParams& q, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 2, row kernel for integer up-sampling factors U in {2, 4, 8} of a cubic grid (the benchmark shapes).
-// One CTA owns one output x index and `cyb` low-res cell rows in y; per chunk of <= `ac` prototypes it
-//   1. interpolates the corner dots in x and y ONCE per (cell row, prototype, low-res z) into shared memory
-//      (4 coalesced loads + 2 + U lerps for U * U * 4 outputs), with the z border clamp pre-applied as padding;
-//   2. lets every thread finish a float4 of outputs along z: per prototype NV shared-memory words, NV-1 differences,
-//      4 FMA + 4 max -- the per-voxel-per-prototype work that bounds the kernel -- and one 16-byte store per class.
-// |interp(f)|^2 = w^T G w is contracted in x per CTA (7 numbers per z cell), in y and z per thread.
-// ---------------------------------------------------------------------------------------------
-template <int U> struct UpPat;
-template <> struct UpPat<2> { static constexpr int NV = 4; __host__ __device__ static constexpr int J(int k) { return (k + 1) >> 1; } };
-template <> struct UpPat<4> { static constexpr int NV = 3; __host__ __device__ static constexpr int J(int k) { return k >> 1; } };
-template <> struct UpPat<8> { static constexpr int NV = 2; __host__ __device__ static constexpr int J(int) { return 0; } };
-constexpr int UP_GPT = 4;      // float4 groups per thread (max)
-
-__device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0 ? a : a - b + 1) / b; }
-
-template <int U>
-__global__ void __launch_bounds__(256) sim_upsample_rows_kernel(UpParams q, int cyb, int rb, int ac, int i0, int ng,
-                                                                int czA, int WZ) {
-    using P = UpPat<U>;
-    extern __shared__ float s_dyn[];
-    const int n = q.w, N = q.W;
-    const int nrow = cyb * rb;                       // output rows of this CTA
-    float* s_rows = s_dyn;                           // [nrow][ac][WZ]   x,y-interpolated dots, z padded/clamped
-    float* s_e = s_rows + nrow * ac * WZ;            // [cyb][WZ][7]     x-contracted corner Gram
-    int* s_off = reinterpret_cast<int*>(s_e + cyb * WZ * 7);
-    const int tid = threadIdx.x;
-    for (int i = tid; i <= q.C; i += 256) s_off[i] = q.class_offsets[i];
-    const int ox = blockIdx.x;
-    const int cx = floor_div(ox - U / 2, U);
-    const float tx = (ox - U / 2 - U * cx + 0.5f) / U;
-    const int x0 = cx < 0 ? 0 : cx, x1 = cx + 1 > n - 1 ? n - 1 : cx + 1;
-    const int cy0 = static_cast<int>(blockIdx.y) * cyb - 1;       // first cell row of the CTA
-    const int ky0 = static_cast<int>(blockIdx.z) * rb;            // first output row inside each cell
-    const int64_t n_lr = static_cast<int64_t>(n) * n * n;
-    auto clampi = [n](int v) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); };
-
-    // ---- x-contracted Gram per (cell row, z corner): E[0..2] same z, (y0,y0) (y0,y1) (y1,y1); E[3..6] z -> z+1 ----
-    if (q.mode == VITTF_SIM_NS) {
-        const float wx[2] = {1.0f - tx, tx};
-        const int xs[2] = {x0, x1};
-        for (int it = tid; it < cyb * WZ * 7; it += 256) {
-            const int e = it % 7, k = (it / 7) % WZ, cl = it / (7 * WZ);
-            const int cy = cy0 + cl;
-            const int ys[2] = {clampi(cy), clampi(cy + 1)};
-            const int za = clampi(czA + k), zb = e < 3 ? za : clampi(czA + k + 1);
-            const int ya = e < 3 ? (e == 2 ? 1 : 0) : ((e - 3) >> 1), yb = e < 3 ? (e == 0 ? 0 : 1) : ((e - 3) & 1);
-            float acc = 0.0f;
-            if (cy <= n - 1) {
-#pragma unroll
-                for (int xa = 0; xa < 2; ++xa)
-#pragma unroll
-                    for (int xb = 0; xb < 2; ++xb) {
-                        bool swap;
-                        const int slot = gram_slot(xs[xb] - xs[xa], ys[yb] - ys[ya], zb - za, swap);
-                        const int64_t va = (static_cast<int64_t>(xs[xa]) * n + ys[ya]) * n + za;
-                        const int64_t vb = (static_cast<int64_t>(xs[xb]) * n + ys[yb]) * n + zb;
-                        acc = fmaf(wx[xa] * wx[xb], __ldg(q.gram + static_cast<int64_t>(slot) * n_lr + (swap ? vb : va)), acc);
-                    }
-            }
-            s_e[it] = acc;
-        }
-    }
-
-    // ---- this thread's float4 groups: row, z cells, weights ----
-    const int total = nrow * ng;
-    int g_row[UP_GPT], g_k0[UP_GPT];
-    int64_t g_out[UP_GPT];
-    float g_tz[UP_GPT][4];
-    bool g_live[UP_GPT];
-#pragma unroll
-    for (int gi = 0; gi < UP_GPT; ++gi) {
-        const int g = tid + gi * 256;
-        g_live[gi] = g < total;
-        const int row = g_live[gi] ? g / ng : 0, i = i0 + (g_live[gi] ? g % ng : 0);
-        const int cl = row / rb, ky = ky0 + row % rb;
-        const int oy = U * (cy0 + cl) + U / 2 + ky;
-        g_live[gi] = g_live[gi] && ky < U && oy >= 0 && oy < N;
-        g_row[gi] = row;
-        const int c0 = floor_div(4 * i - U / 2, U);
-        g_k0[gi] = c0 - czA;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) g_tz[gi][k] = (4 * i + k - U / 2 - U * (c0 + P::J(k)) + 0.5f) / U;
-        g_out[gi] = (static_cast<int64_t>(ox) * q.H + oy) * (q.z1 - q.z0) + (4 * i - q.z0);
-    }
-    __syncthreads();
-
-    float g_inv[UP_GPT][4];
-#pragma unroll
-    for (int gi = 0; gi < UP_GPT; ++gi) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) g_inv[gi][k] = 1.0f;
-        if (q.mode != VITTF_SIM_NS || !g_live[gi]) continue;
-        const int row = g_row[gi];
-        const float ty = (ky0 + row % rb + 0.5f) / U;
-        const float a = 1.0f - ty, b = ty;
-        const float* e = s_e + (static_cast<int64_t>(row / rb) * WZ + g_k0[gi]) * 7;
-        float k00[P::NV], k01[P::NV - 1];
-#pragma unroll
-        for (int j = 0; j < P::NV; ++j) {
-            const float* ej = e + j * 7;
-            k00[j] = a * a * ej[0] + 2.0f * a * b * ej[1] + b * b * ej[2];
-            if (j < P::NV - 1) k01[j] = a * a * ej[3] + a * b * (ej[4] + ej[5]) + b * b * ej[6];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float t = g_tz[gi][k], u = 1.0f - t;
-            const float n2 = u * u * k00[P::J(k)] + 2.0f * u * t * k01[P::J(k)] + t * t * k00[P::J(k) + 1];
-            g_inv[gi][k] = 1.0f / fmaxf(sqrtf(fmaxf(n2, 0.0f)), 1e-12f);     // F.normalize eps
-        }
-    }
-
-    // ---- prototypes in chunks; classes are contiguous prototype ranges and may straddle chunks ----
-    const int64_t n_out = static_cast<int64_t>(q.W) * q.H * (q.z1 - q.z0);
-    float best[UP_GPT][4];
-#pragma unroll
-    for (int gi = 0; gi < UP_GPT; ++gi)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) best[gi][k] = -INFINITY;
-    int cls = 0;
-    auto finish_class = [&](int c) {
-#pragma unroll
-        for (int gi = 0; gi < UP_GPT; ++gi) {
-            if (g_live[gi]) {
-                float r[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) r[k] = pow_unit(fminf(fmaxf(best[gi][k] * g_inv[gi][k], 0.0f), 1.0f), q.exponent);
-                float* dst = q.out + static_cast<int64_t>(c) * n_out + g_out[gi];
-                const int oz = static_cast<int>(g_out[gi] % (q.z1 - q.z0));   // unused when fully inside
-                (void)oz;
-                const int z_first = 4 * (i0 + (tid + gi * 256) % ng);
-                if (z_first >= q.z0 && z_first + 4 <= q.z1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                    *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (z_first + k >= q.z0 && z_first + k < q.z1) dst[k] = r[k];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) best[gi][k] = -INFINITY;
-        }
-    };
-    for (int a0 = 0; a0 < q.A; a0 += ac) {
-        const int na = min(ac, q.A - a0);
-        __syncthreads();                                   // previous chunk fully consumed
-        // phase 1: entries (cell row, prototype, padded z index)
-        for (int it = tid; it < cyb * na * WZ; it += 256) {
-            const int k = it % WZ, aa = (it / WZ) % na, cl = it / (WZ * na);
-            const int cy = cy0 + cl;
-            if (cy > n - 1) continue;
-            const int y0 = clampi(cy), y1 = clampi(cy + 1), z = clampi(czA + k);
-            const float* da = q.dots + static_cast<int64_t>(a0 + aa) * n_lr;
-            const float v00 = __ldg(da + (static_cast<int64_t>(x0) * n + y0) * n + z);
-            const float v10 = __ldg(da + (static_cast<int64_t>(x1) * n + y0) * n + z);
-            const float v01 = __ldg(da + (static_cast<int64_t>(x0) * n + y1) * n + z);
-            const float v11 = __ldg(da + (static_cast<int64_t>(x1) * n + y1) * n + z);
-            const float r0 = fmaf(tx, v10 - v00, v00), r1 = fmaf(tx, v11 - v01, v01);
-            const float dr = r1 - r0;
-            for (int rr = 0; rr < rb; ++rr) {
-                const float ty = (ky0 + rr + 0.5f) / U;
-                s_rows[(static_cast<int64_t>(cl * rb + rr) * ac + aa) * WZ + k] = fmaf(ty, dr, r0);
-            }
-        }
-        __syncthreads();
-        // phase 2
-        for (int aa = 0; aa < na; ++aa) {
-            const int a = a0 + aa;
-            while (cls < q.C && a >= s_off[cls + 1]) finish_class(cls++);
-#pragma unroll
-            for (int gi = 0; gi < UP_GPT; ++gi) {
-                if (!g_live[gi]) continue;
-                const float* rp = s_rows + (static_cast<int64_t>(g_row[gi]) * ac + aa) * WZ + g_k0[gi];
-                float v[P::NV], dv[P::NV - 1];
-#pragma unroll
-                for (int j = 0; j < P::NV; ++j) v[j] = rp[j];
-#pragma unroll
-                for (int j = 0; j < P::NV - 1; ++j) dv[j] = v[j + 1] - v[j];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) best[gi][k] = fmaxf(best[gi][k], fmaf(g_tz[gi][k], dv[P::J(k)], v[P::J(k)]));
-            }
-        }
-    }
-    while (cls < q.C) finish_class(cls++);
-}
-
-template <int U>
-int launch_rows(const UpParams& q, cudaStream_t s) {
-    const int n = q.w, N = q.W;
-    const int i0 = q.z0 / 4, i1 = ceil_div(q.z1, 4), ng = i1 - i0;
-    auto fdiv = [](int a, int b) { return (a >= 0 ? a : a - b + 1) / b; };
-    const int czA = fdiv(4 * i0 - U / 2, U), czB = fdiv(4 * i1 - 1 - U / 2, U);
-    const int WZ = czB - czA + 2 + (UpPat<U>::NV - 2);     // + slack so that every group may read NV words
-    // rows per cell per CTA (rb) and cell rows per CTA (cyb): up to UP_GPT * 256 float4 groups per CTA
-    int rb = U;
-    while (rb > 1 && rb * ng > UP_GPT * 256) rb /= 2;
-    if (rb * ng > UP_GPT * 256) return -1;                  // caller falls back to the generic kernel
-    int cyb = 256 / (rb * ng);
-    if (cyb < 1) cyb = 1;
-    if (cyb > 8) cyb = 8;
-    int ac = q.A < 32 ? q.A : 32;
-    auto bytes = [&](int ac_) { return (static_cast<size_t>(cyb) * rb * ac_ * WZ + static_cast<size_t>(cyb) * WZ * 7 + q.C + 1) * 4; };
-    while (ac > 1 && bytes(ac) > 96 * 1024) ac /= 2;
-    if (bytes(ac) > 200 * 1024) return -1;
-    auto kern = sim_upsample_rows_kernel<U>;
-    static PerDeviceMemo configured;
-    if (bytes(ac) > configured.cur()) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes(ac))) != cudaSuccess) return -1;
-        configured.cur() = bytes(ac);
-    }
-    dim3 grid(N, ceil_div(n + 1, cyb), U / rb);
-    kern<<<grid, 256, bytes(ac), s>>>(q, cyb, rb, ac, i0, ng, czA, WZ);
-    return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
 __global__ void class_max_init_kernel(float* out, int C) {
     if (threadIdx.x < C) out[threadIdx.x] = -INFINITY;
 }
@@ -1903,32 +1105,6 @@ __global__ void __launch_bounds__(256) labels_kernel(const T* __restrict__ sims,
     }
 }
 
-template <bool GRAM>
-int launch_lowres_tiled(const __half* feats, int F, int w, int h, int d, const float* protos, int A, float* dots,
-                        float* gram, cudaStream_t s) {
-    dim3 grid(ceil_div(d, TB_Z), ceil_div(h, TB_Y), ceil_div(w, TB_X));
-    bool first = true;
-    for (int a_base = 0; a_base < A || first; first = false) {
-        const int rem = A - a_base;
-        if (rem > 16) {
-            if (first && GRAM) sim_lowres_tiled_kernel<32, true><<<grid, 256, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
-            else sim_lowres_tiled_kernel<32, false><<<grid, 256, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
-            a_base += 32;
-        } else if (rem > 8) {
-            if (first && GRAM) sim_lowres_tiled_kernel<16, true><<<grid, 256, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
-            else sim_lowres_tiled_kernel<16, false><<<grid, 256, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
-            a_base += 16;
-        } else {
-            if (first && GRAM) sim_lowres_tiled_kernel<8, true><<<grid, 256, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
-            else sim_lowres_tiled_kernel<8, false><<<grid, 256, 0, s>>>(feats, F, w, h, d, protos, A, a_base, dots, gram);
-            a_base += 8;
-        }
-        vittf_count_launches(1);
-    }
-    VITTF_CHECK_CUDA(cudaGetLastError());
-    return VITTF_OK;
-}
-
 template <typename T, bool GRAM>
 int launch_lowres(const T* feats, int F, int w, int h, int d, const float* protos, int A, float* dots, float* gram,
                   cudaStream_t s) {
@@ -1980,29 +1156,35 @@ extern "C" int vittf_sample_prototypes(const void* feats, int feat_dtype, int F,
     return VITTF_OK;
 }
 
+// One A/B switch for the whole stage: VITTF_SIM_GENERIC forces the generic kernels of both passes (any dtype / shape / mode),
+// which a test exercises against the same oracle as the tensor-core paths.
+static bool sim_generic_only() {
+    static const bool on = getenv("VITTF_SIM_GENERIC") != nullptr;
+    return on;
+}
+
 extern "C" int vittf_sim_lowres_layout(int feat_dtype, int F, int w, int h, int d, const void* feats) {
-    static const bool off = getenv("VITTF_SIM_NO_MMA") != nullptr || getenv("VITTF_SIM_NO_FUSED") != nullptr || getenv("VITTF_SIM_NO_TMA") != nullptr;
     const size_t panel = static_cast<size_t>(32) * (F + 8) * 2;
-    return !off && feat_dtype == VITTF_F16 && F > 0 && F % DM_BK == 0 && d % 8 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0 &&
-           static_cast<size_t>(F) * 16 * 4 <= 96 * 1024 && (220 * 1024 - panel - 256) / GM_STAGE >= 3;
+    return !sim_generic_only() && feat_dtype == VITTF_F16 && F > 0 && F % DM_BK == 0 && d % 8 == 0 &&
+           (reinterpret_cast<uintptr_t>(feats) & 15) == 0 && (220 * 1024 - panel - 256) / GM_STAGE >= 3;
 }
 
 extern "C" int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w, int h, int d, const float* protos, int A,
                                 float* dots, float* gram, int dots_layout, void* stream) {
     VITTF_REQUIRE(feats && protos && dots, "vittf_sim_lowres: null pointer");
     VITTF_REQUIRE(F > 0 && w > 0 && h > 0 && d > 0 && A > 0, "vittf_sim_lowres: empty problem");
-    VITTF_REQUIRE(dots_layout == 0 || (dots_layout == 1 && vittf_sim_lowres_layout(feat_dtype, F, w, h, d, feats)),
+    const bool fused = vittf_sim_lowres_layout(feat_dtype, F, w, h, d, feats) != 0;
+    VITTF_REQUIRE(dots_layout == 0 || (dots_layout == 1 && fused),
                   "vittf_sim_lowres: dots_layout %d is not available for this input (ask vittf_sim_lowres_layout)", dots_layout);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (fused) {
+        // fp16 features, F % 32 == 0, d % 8 == 0: dots + Gram from one read of the volume on the tensor cores
+        const int rc = launch_lowres_mma(static_cast<const __half*>(feats), F, w, h, d, protos, A, dots, gram, s, dots_layout);
+        if (rc != -1) return rc;
+        VITTF_REQUIRE(dots_layout == 0, "vittf_sim_lowres: fused pass unavailable for F=%d", F);
+    }
     if (feat_dtype == VITTF_F16) {
         const __half* f = static_cast<const __half*>(feats);
-        static const bool no_tma = getenv("VITTF_SIM_NO_TMA") != nullptr;     // A/B switch: previous tiled kernel
-        if (!no_tma && d % 8 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 && static_cast<size_t>(F) * 16 * 4 <= 96 * 1024)
-            return gram ? launch_lowres_tma<true>(f, F, w, h, d, protos, A, dots, gram, s, dots_layout)
-                        : launch_lowres_tma<false>(f, F, w, h, d, protos, A, dots, gram, s, dots_layout);
-        if (d % 2 == 0 && (reinterpret_cast<uintptr_t>(f) & 1) == 0)   // z pairs share a 4-byte word
-            return gram ? launch_lowres_tiled<true>(f, F, w, h, d, protos, A, dots, gram, s)
-                        : launch_lowres_tiled<false>(f, F, w, h, d, protos, A, dots, gram, s);
         return gram ? launch_lowres<__half, true>(f, F, w, h, d, protos, A, dots, gram, s)
                     : launch_lowres<__half, false>(f, F, w, h, d, protos, A, dots, gram, s);
     } else if (feat_dtype == VITTF_F32) {
@@ -2025,54 +1207,33 @@ extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, i
     VITTF_REQUIRE(C > 0 && A > 0 && W > 0 && H > 0 && D > 0 && z0 >= 0 && z1 > z0 && z1 <= D,
                   "vittf_sim_upsample: bad sizes (C=%d A=%d out=%dx%dx%d z=[%d,%d))", C, A, W, H, D, z0, z1);
     UpParams q{dots, gram, class_offsets, out, w, h, d, A, C, W, H, D, z0, z1, mode, threshold, exponent};
-    // integer power-of-two up-sampling of a cubic grid, max-type modes: separable cell kernel
-    const bool cubic = w == h && h == d && W == H && H == D && W % w == 0;
-    const int U = cubic ? W / w : 0;
-    // any grid whose three factors are the same U in {2, 4, 8}: tcgen05 cell-tile kernel (sim_up_tc.cu)
-    static const bool no_tc = getenv("VITTF_SIM_UP_NO_TC") != nullptr;         // A/B switch: previous mma.sync kernel
-    if (mode == VITTF_SIM_NS && (!no_tc || dots_layout == 1) && vittf_launch_upsample_tc(q, dots_layout, static_cast<cudaStream_t>(stream)) == 0) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dots_layout == 1) {
+        // voxel-major dots: NS mode with one integer factor 2 / 4 / 8 on the tcgen05 cell-tile kernel (sim_up_tc.cu)
+        VITTF_REQUIRE(mode == VITTF_SIM_NS && vittf_launch_upsample_tc(q, dots_layout, s) == 0,
+                      "vittf_sim_upsample: the voxel-major dots layout is only read by the tcgen05 kernel (NS mode, factor 2 / 4 / 8)");
         VITTF_CHECK_CUDA(cudaGetLastError());
         vittf_count_launches(1);
         return VITTF_OK;
     }
-    VITTF_REQUIRE(dots_layout == 0, "vittf_sim_upsample: the voxel-major dots layout is only read by the tcgen05 kernel (NS mode, factor 2 / 4 / 8)");
-    if (mode == VITTF_SIM_NS && (W == 4 * w || W == 8 * w) && H * static_cast<int64_t>(w) == static_cast<int64_t>(h) * W &&
+    // NS mode, one factor 4 or 8 on all three axes: warp-level mma.sync cell-tile kernel (cheaper per prototype than the
+    // tcgen05 kernel: no TMEM round trip per prototype -- profiles/r2_sim_kernels.md)
+    if (!sim_generic_only() && mode == VITTF_SIM_NS && (W == 4 * w || W == 8 * w) && H * static_cast<int64_t>(w) == static_cast<int64_t>(h) * W &&
         D * static_cast<int64_t>(w) == static_cast<int64_t>(d) * W && static_cast<int64_t>(W) * H * (z1 - z0) < (1ll << 30) &&
         static_cast<int64_t>(w) * h * d < (1ll << 31)) {
-        static const bool no_mma = getenv("VITTF_SIM_UP_NO_MMA") != nullptr;   // A/B switch: FMA-pipe cell kernel
-        if (!no_mma) {
-            cudaStream_t s = static_cast<cudaStream_t>(stream);
-            const int rc = W == 4 * w ? launch_upsample_mma<4>(q, s) : launch_upsample_mma<8>(q, s);
-            if (rc == 0) {
-                VITTF_CHECK_CUDA(cudaGetLastError());
-                vittf_count_launches(1);
-                return VITTF_OK;
-            }
-        }
-    }
-    if (cubic && mode != VITTF_SIM_REFNTF && (U == 2 || U == 4 || U == 8) && mode == VITTF_SIM_NS) {
-        static const bool use_rows = getenv("VITTF_SIM_ROWS") != nullptr;    // A/B switch: shared-memory row kernel
-        cudaStream_t s = static_cast<cudaStream_t>(stream);
-        int rc = -1;
-        if (w % 32 == 0 && !use_rows) {
-            if (U == 2) launch_cells<2>(q, s);
-            else if (U == 4) launch_cells<4>(q, s);
-            else launch_cells<8>(q, s);
-            rc = 0;
-        } else {
-            rc = U == 2 ? launch_rows<2>(q, s) : U == 4 ? launch_rows<4>(q, s) : launch_rows<8>(q, s);
-        }
+        const int rc = W == 4 * w ? launch_upsample_mma<4>(q, s) : launch_upsample_mma<8>(q, s);
         if (rc == 0) {
             VITTF_CHECK_CUDA(cudaGetLastError());
             vittf_count_launches(1);
             return VITTF_OK;
         }
     }
+    // every other scale factor, mode and shape
     const int64_t n_out = static_cast<int64_t>(W) * H * (z1 - z0);
     int64_t blocks = ceil_div_ll(n_out, 256);
     const int64_t cap = static_cast<int64_t>(vittf_num_sms()) * 32;
     if (blocks > cap) blocks = cap;
-    sim_upsample_kernel<<<static_cast<unsigned>(blocks), 256, (C + 1) * sizeof(int), static_cast<cudaStream_t>(stream)>>>(q);
+    sim_upsample_kernel<<<static_cast<unsigned>(blocks), 256, (C + 1) * sizeof(int), s>>>(q);
     VITTF_CHECK_CUDA(cudaGetLastError());
     vittf_count_launches(1);
     return VITTF_OK;

@@ -10,6 +10,9 @@ import torch
 import torch.nn as nn
 
 ARCHS = {"vits16": (384, 12, 6, 16), "vits8": (384, 12, 6, 8), "vitb16": (768, 12, 12, 16), "vitb8": (768, 12, 12, 8)}
+# DINOv2 (infer.py:45-46,254-260; hub 'facebookresearch/dinov2' dinov2_vit{s,b,l}14): patch 14, 518^2 training size (37 x 37
+# position grid), LayerScale after attention and MLP (blocks[i].ls1.gamma / ls2.gamma).  vitg14 (SwiGLU FFN, 1536-d) is not built.
+ARCHS_V2 = {"vits14": (384, 12, 6, 14), "vitb14": (768, 12, 12, 14), "vitl14": (1024, 24, 16, 14)}
 
 
 class _Attn(nn.Module):
@@ -27,13 +30,22 @@ class _Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden, dim)
 
 
+class _LayerScale(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+
+
 class _Block(nn.Module):
-    def __init__(self, dim, heads):
+    def __init__(self, dim, heads, layer_scale=False):
         super().__init__()
         self.norm1 = nn.LayerNorm(dim, eps=1e-6)
         self.attn = _Attn(dim, heads)
         self.norm2 = nn.LayerNorm(dim, eps=1e-6)
         self.mlp = _Mlp(dim, 4 * dim)
+        if layer_scale:
+            self.ls1 = _LayerScale(dim)
+            self.ls2 = _LayerScale(dim)
 
 
 class _PatchEmbed(nn.Module):
@@ -45,13 +57,16 @@ class _PatchEmbed(nn.Module):
 class DinoWeights(nn.Module):
     def __init__(self, name):
         super().__init__()
-        dim, depth, heads, patch = ARCHS[name]
+        v2 = name in ARCHS_V2
+        dim, depth, heads, patch = (ARCHS_V2 if v2 else ARCHS)[name]
         self.embed_dim = dim
         self.patch_embed = _PatchEmbed(patch, dim)
-        grid = 224 // patch
+        grid = (518 if v2 else 224) // patch
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, grid * grid + 1, dim))
-        self.blocks = nn.ModuleList([_Block(dim, heads) for _ in range(depth)])
+        self.blocks = nn.ModuleList([_Block(dim, heads, layer_scale=v2) for _ in range(depth)])
+        if v2:
+            self.mask_token = nn.Parameter(torch.zeros(1, dim))
         self.norm = nn.LayerNorm(dim, eps=1e-6)
 
     def forward(self, *a, **k):
@@ -92,6 +107,8 @@ def build_dino(name, weights=None, seed=0):
         elif isinstance(mod, nn.LayerNorm):
             nn.init.ones_(mod.weight)
             nn.init.zeros_(mod.bias)
+        elif isinstance(mod, _LayerScale):
+            nn.init.uniform_(mod.gamma, 0.5, 1.5)            # (hub init is 1.0; random so that the folding is visible in tests)
     torch.random.set_rng_state(gen_state)
     if weights is not None:
         sd = torch.load(weights, map_location="cpu", weights_only=False)

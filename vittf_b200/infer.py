@@ -301,18 +301,22 @@ def load_data(data_path):
 
 
 def load_model(args):
-    """infer.py:239-264 (DINO v1 archs; the reference's DINOv2 branch is broken, SURVEY.md §0.4 #5)."""
+    """infer.py:239-264: DINO v1 (patch 8 / 16) and DINOv2 (patch 14) backbones."""
     if not args.dino_model and not args.dino2_model:
         print('No DINO/DINOv2 model specified, using default: vits8')
         args.dino_model = 'vits8'
     elif args.dino_model and args.dino2_model:
         print('Both --dino-model and --dino2-model were set. Please only set one of them.')
         sys.exit(1)
-    elif args.dino2_model:
-        print('DINOv2 backbones are not supported by vittf_b200 (out of scope, SURVEY.md §8f).')
-        sys.exit(1)
+    from .dino import ARCHS_V2, build_dino
+    if args.dino2_model:                                   # infer.py:254-260 (as intended: the reference's branch has a typo, :258)
+        if args.dino2_model not in ARCHS_V2:
+            print(f'DINOv2 {args.dino2_model} (SwiGLU feed-forward, 1536-d) is not built; available: {sorted(ARCHS_V2)}.')
+            sys.exit(1)
+        args.dino_model = args.dino2_model
+        args.model = args.dino2_model
+        return args.dino2_model, build_dino, 14
     args.model = args.dino_model
-    from .dino import build_dino
     return args.dino_model, build_dino, 8 if args.dino_model[-1] == '8' else 16
 
 

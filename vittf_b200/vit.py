@@ -93,12 +93,23 @@ class VitEngine:
         for i, blk in enumerate(blocks):
             qkv_w = blk.attn.qkv.weight.detach().float().cpu() * q_scale[:, None]
             qkv_b = blk.attn.qkv.bias.detach().float().cpu() * q_scale
+            proj_w, proj_b = blk.attn.proj.weight.detach().float().cpu(), blk.attn.proj.bias.detach().float().cpu()
+            fc2_w, fc2_b = blk.mlp.fc2.weight.detach().float().cpu(), blk.mlp.fc2.bias.detach().float().cpu()
+            # DINOv2 LayerScale (x + gamma * f(x)): a per-output-channel factor of the projection that precedes it -- folded
+            # into its weight rows and bias in fp32 before the bf16 copy
+            mods = blk._modules
+            if "ls1" in mods and hasattr(mods["ls1"], "gamma"):
+                g1 = mods["ls1"].gamma.detach().float().cpu()
+                proj_w, proj_b = proj_w * g1[:, None], proj_b * g1
+            if "ls2" in mods and hasattr(mods["ls2"], "gamma"):
+                g2 = mods["ls2"].gamma.detach().float().cpu()
+                fc2_w, fc2_b = fc2_w * g2[:, None], fc2_b * g2
             fields = dict(ln1_w=f32(blk.norm1.weight), ln1_b=f32(blk.norm1.bias),
                           qkv_w=bf16(qkv_w), qkv_b=f32(qkv_b),
-                          proj_w=bf16(blk.attn.proj.weight), proj_b=f32(blk.attn.proj.bias),
+                          proj_w=bf16(proj_w), proj_b=f32(proj_b),
                           ln2_w=f32(blk.norm2.weight), ln2_b=f32(blk.norm2.bias),
                           fc1_w=bf16(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias),
-                          fc2_w=bf16(blk.mlp.fc2.weight), fc2_b=f32(blk.mlp.fc2.bias))
+                          fc2_w=bf16(fc2_w), fc2_b=f32(fc2_b))
             for k, v in fields.items():
                 setattr(arr[i], k, v.data_ptr())
         self._blocks = arr
