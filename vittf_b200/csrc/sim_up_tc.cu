@@ -221,12 +221,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sim_upsample_tc_kernel(TcParams
                         ptx::tc_fence_after();
                         const uint32_t a_t = tmem_base + TC_COL_A + st * TC_STAGE_COLS + 32 * q;
                         const uint32_t d_t = tmem_base + buf * TC_BUF_COLS;
+#ifndef TC_EXP_NO_MMA
 #pragma unroll
                         for (int s = 0; s < NSL; ++s) umma_ts_tf32(d_t, a_t + 8 * s, b_desc + 2 * s, idesc, s != 0);
                         if (U == 8) {
 #pragma unroll
                             for (int s = 0; s < KC / 8; ++s) umma_ts_tf32(d_t, a_t + 8 * s, b_desc + 2 * (NSL + s), idesc, 1);
                         }
+#else
+                        (void)a_t; (void)d_t; (void)b_desc; (void)idesc;
+#endif
                         ptx::tc_commit(&d_full[buf]);
                         TC_TRACE(1, g);
                     }
@@ -448,9 +452,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sim_upsample_tc_kernel(TcParams
                             warp_wait(&a_empty[st], ((g / TC_STAGES) & 1) ^ 1);
                             ptx::tc_fence_after();
                             const uint32_t dst = t_a + st * TC_STAGE_COLS;
+#ifndef TC_EXP_NO_PROD
                             put_row(x[2 * pr], dst);
                             if (a + 1 < p.A) put_row(x[2 * pr + 1], dst + 32);
                             ptx::tc_wait_st();
+#else
+                            (void)dst;
+#endif
                             ptx::tc_fence_before();
                             ptx::mbar_arrive(&a_full[st]);
                             if (r == 0) TC_TRACE(0, 2 * g);
@@ -552,16 +560,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sim_upsample_tc_kernel(TcParams
                 uint32_t v0[CW];
                 warp_wait(&d_full[buf], (g / TC_NBUF) & 1);
                 ptx::tc_fence_after();
+#ifndef TC_EXP_NO_LD
                 if constexpr (CW == 32) ptx::tmem_ld32(t_d, v0);
                 else ptx::tmem_ld16(t_d, v0);
+#else
+#pragma unroll
+                for (int i = 0; i < CW; ++i) v0[i] = t_d + i;
+#endif
                 if (two) {
                     const uint32_t buf1 = (g + 1) % TC_NBUF;
                     const uint32_t t_d1 = tmem_base + lane_base + buf1 * TC_BUF_COLS + col0;
                     uint32_t u0[CW];
                     warp_wait(&d_full[buf1], ((g + 1) / TC_NBUF) & 1);
                     ptx::tc_fence_after();
+#ifndef TC_EXP_NO_LD
                     if constexpr (CW == 32) ptx::tmem_ld32(t_d1, u0);
                     else ptx::tmem_ld16(t_d1, u0);
+#else
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) u0[i] = t_d1 + i;
+#endif
                     ptx::tc_wait_ld();
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(&d_empty[buf]);
