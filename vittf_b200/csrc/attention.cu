@@ -659,6 +659,23 @@ int attention_launch(const void* qk, const void* vt, void* out, int B, int token
 }
 }  // namespace
 
+static void attn_trace_dump() {
+#ifdef ATTN_TRACE
+    if (getenv("VITTF_ATTN_TRACE_DUMP")) {
+        static long long h[3 * 40 * 4];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
+        long long t0 = h[0];
+        for (int r = 0; r < 3; ++r)
+            for (int j = 2; j < 14; ++j) {
+                printf("role %d blk %2d:", r, j);
+                for (int k = 0; k < 4; ++k) printf(" %7lld", h[(r * 40 + j) * 4 + k] - t0);
+                printf("\n");
+            }
+    }
+#endif
+}
+
 extern "C" int64_t vittf_attention_workspace_bytes(int B, int tokens, int heads) {
     if (B <= 0 || tokens <= 0 || heads <= 0) return -1;
     return static_cast<int64_t>(ceil_div(tokens, 2 * BQ)) * heads * B * sizeof(int);
@@ -681,6 +698,7 @@ extern "C" int vittf_attention_prescaled(const void* qk, const void* vt, void* o
     if (safe_only) return attention_launch(qk, vt, out, B, tokens, tok_pad, heads, 1.0f, nullptr, false, s);
     VITTF_CHECK_CUDA(cudaMemsetAsync(flags, 0, need, s));
     VITTF_CHECK(attention_launch(qk, vt, out, B, tokens, tok_pad, heads, 1.0f, flags, true, s));
+    attn_trace_dump();
     return attention_launch(qk, vt, out, B, tokens, tok_pad, heads, 1.0f, flags, false, s);
 }
 
@@ -692,19 +710,6 @@ extern "C" int vittf_attention(const void* qk, const void* vt, void* out, int B,
                   tok_pad);
     VITTF_CHECK(attention_launch(qk, vt, out, B, tokens, tok_pad, heads, 0.125f * 1.4426950408889634f, nullptr, false,
                                  static_cast<cudaStream_t>(stream)));
-#ifdef ATTN_TRACE
-    if (getenv("VITTF_ATTN_TRACE_DUMP")) {
-        static long long h[3 * 40 * 4];
-        cudaDeviceSynchronize();
-        cudaMemcpyFromSymbol(h, g_trace, sizeof(h));
-        long long t0 = h[0];
-        for (int r = 0; r < 3; ++r)
-            for (int j = 2; j < 10; ++j) {
-                printf("role %d blk %2d:", r, j);
-                for (int k = 0; k < 4; ++k) printf(" %7lld", h[(r * 40 + j) * 4 + k] - t0);
-                printf("\n");
-            }
-    }
-#endif
+    attn_trace_dump();
     return VITTF_OK;
 }

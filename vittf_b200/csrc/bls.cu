@@ -124,15 +124,48 @@ __global__ void __launch_bounds__(256) splat_kernel(Grid g, int z0, int zs, cons
     __syncthreads();
     const int64_t n = static_cast<int64_t>(g.W) * g.H * zs;
     const float cm = c_max ? *c_max : 0.0f;
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int z = z0 + static_cast<int>(i % zs), y = static_cast<int>((i / zs) % g.H), x = static_cast<int>(i / (static_cast<int64_t>(zs) * g.H));
-        const int64_t cell = cell_of(g, x, y, z, s_lut[__ldg(r + (static_cast<int64_t>(x) * g.H + y) * g.D + z)]);
-        const double c = static_cast<double>(c_max ? cm - conf[i] : conf[i]);
-        double* a = acc + cell * (2 + nrhs);
-        atomicAdd(a, 1.0);
-        atomicAdd(a + 1, c);
-        for (int k = 0; k < nrhs; ++k) atomicAdd(a + 2 + k, static_cast<double>(t[k * n + i]) * c);
+    const int lane = threadIdx.x & 31;
+    const int stride = 2 + nrhs;
+    // Lanes are z-adjacent voxels, so several of them fall into the same cell (one spatial bin is 7 voxels long): the L2
+    // atomic units are what bounds this kernel (195 G fp64 atomics / s measured), so lanes with equal cells first add up
+    // inside the warp (match_any + a rank tree over the peer set) and only the first of them issues the 2 + nrhs atomics.
+    for (int64_t i0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) - lane; i0 < n;
+         i0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t i = i0 + lane;
+        const bool valid = i < n;
+        long long cell = -1 - lane;                                   // invalid lanes: unique keys, never written
+        double c = 0.0;
+        if (valid) {
+            const int z = z0 + static_cast<int>(i % zs), y = static_cast<int>((i / zs) % g.H), x = static_cast<int>(i / (static_cast<int64_t>(zs) * g.H));
+            cell = cell_of(g, x, y, z, s_lut[__ldg(r + (static_cast<int64_t>(x) * g.H + y) * g.D + z)]);
+            c = static_cast<double>(c_max ? cm - conf[i] : conf[i]);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, cell);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned partner[5];
+#pragma unroll
+        for (int s5 = 0; s5 < 5; ++s5) partner[s5] = __fns(peers, lane, (1 << s5) + 1);       // peer `1 << s5` ranks above, or ~0
+        auto seg_sum = [&](double v) {
+#pragma unroll
+            for (int s5 = 0; s5 < 5; ++s5) {
+                const bool take = partner[s5] != 0xffffffffu && (rank & ((2 << s5) - 1)) == 0;
+                const double o = __shfl_sync(0xffffffffu, v, take ? static_cast<int>(partner[s5]) : lane);
+                if (take) v += o;
+            }
+            return v;
+        };
+        const double cnt = seg_sum(valid ? 1.0 : 0.0);
+        const double csum = seg_sum(c);
+        double* a = acc + (cell > 0 ? cell : 0) * stride;
+        const bool lead = valid && rank == 0;
+        if (lead) {
+            atomicAdd(a, cnt);
+            atomicAdd(a + 1, csum);
+        }
+        for (int k = 0; k < nrhs; ++k) {
+            const double bk = seg_sum(valid ? static_cast<double>(t[k * n + i]) * c : 0.0);
+            if (lead) atomicAdd(a + 2 + k, bk);
+        }
     }
 }
 
