@@ -246,7 +246,7 @@ def bench_similarity_sweep(args, rank, world, dev, dist):
     feats_h, protos_c = synth.class_features(384, (lr,) * 3, 8, seed=0)
     feats_h = feats_h.pin_memory()
     feats = feats_h.to(dev)
-    zr = vdist.z_range(out, world, rank)
+    xr = vdist.x_range(out, world, rank)          # x-slabs: pass 1 (dots + Gram) shards with the maps, no exchange
     peaks = _peaks()
     hbm = peaks.get("hbm_gbs", 6650.0)
     warm = max(3, args.warmup)
@@ -259,7 +259,7 @@ def bench_similarity_sweep(args, rank, world, dev, dist):
         offs = torch.tensor(offs_l, dtype=torch.int32, device=dev)
 
         def run():
-            return similarity_maps(feats, p, offs, (out,) * 3, mode="ns", z_range=zr)
+            return similarity_maps(feats, p, offs, (out,) * 3, mode="ns", x_range=xr)
         for _ in range(warm):
             run()
         is_head = A == SWEEP_A[-1]
@@ -279,8 +279,8 @@ def bench_similarity_sweep(args, rank, world, dev, dist):
             def e2e():
                 nonlocal maps_host
                 f = feats_h.to(dev, non_blocking=True)                       # H2D of the cached feature volume
-                sims = similarity_maps(f, p, offs, (out,) * 3, mode="ns", z_range=zr)
-                q, _ = pipeline.quantized_maps(sims, zr, out)
+                sims = similarity_maps(f, p, offs, (out,) * 3, mode="ns", x_range=xr)
+                q, _ = pipeline.quantized_maps(sims, (0, out), out)          # (slab bounds are even: half-resolution rows stay local)
                 if maps_host is None:
                     maps_host = torch.empty(q.shape, dtype=torch.uint8).pin_memory()
                 maps_host.copy_(q, non_blocking=True)                        # what compute_similarities returns
@@ -294,7 +294,8 @@ def bench_similarity_sweep(args, rank, world, dev, dist):
             "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": head["ms"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16 features, f32 accumulate / maps",
             "data": "synthetic",
-            "config": {"workload": CFG4_TEXT, "parallelism": f"output z-slabs over {world} GPU(s), feature volume replicated",
+            "config": {"workload": CFG4_TEXT, "parallelism": f"output x-slabs over {world} GPU(s): each rank evaluates the low-res planes under its "
+                       "slab +- 1 (no exchange), feature volume replicated",
                        "l2": "1.61 GB of features and 4.3 GB of maps per pass exceed the 126 MB L2"},
             "e2e": {"value": out ** 3 / head["ms_e2e"] / 1e6, "unit": "Gvoxel/s", "h2d_bytes_per_step": feats_h.numel() * 2,
                     "d2h_bytes_per_step": head["d2h"], "ms": head["ms_e2e"]},

@@ -165,10 +165,13 @@ int vittf_sample_prototypes(const void* feats, int feat_dtype, int F, int w, int
  *                             without materialising interp(f).
  *   dots_layout 0: dots fp32 (A, n_lr).  1: dots fp32 (n_lr, A4) with A4 = A rounded up to a multiple of 4 (voxel-major: the
  *   tcgen05 up-sampling kernel gathers the corner dots of 4 prototypes with one 16-byte load); only the fused tensor-core pass
- *   writes it -- vittf_sim_lowres_layout() tells whether it is available for an input (1) or not (0). */
+ *   writes it -- vittf_sim_lowres_layout() tells whether it is available for an input (1) or not (0).
+ */
 int vittf_sim_lowres_layout(int feat_dtype, int F, int w, int h, int d, const void* feats);
+/*   [xa, xb): low-res x planes to evaluate (slab sharding, SURVEY.md 8e: a rank only needs the planes under its output
+ *   slab +- 1; the other planes of dots / gram are left untouched).  The generic fallback kernels evaluate every plane. */
 int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w, int h, int d, const float* protos, int A,
-                     float* dots, float* gram, int dots_layout, void* stream);
+                     float* dots, float* gram, int dots_layout, int xa, int xb, void* stream);
 
 typedef enum {
     VITTF_SIM_NS = 0,     /* interp(features) -> L2 normalise -> dot -> clamp(0,1)^e -> class MAX */
@@ -179,11 +182,12 @@ typedef enum {
 
 /* Second pass: per OUTPUT voxel combine the 8 surrounding low-res dots (trilinear,
  * align_corners=False index rule of F.interpolate), normalise, non-linearity, per-class
- * reduction.  Output z-range [z0,z1) of the (W,H,D) grid only (z-slab sharding, §8e):
- * out fp32 (C, W, H, z1-z0).  For REFNTF/LEGACY the output grid equals the low-res grid.
+ * reduction.  Output slab [x0,x1) x [z0,z1) of the (W,H,D) grid only (slab sharding, §8e): z-slabs as in north_star, x-slabs
+ * (the slowest axis: every class map of a rank is one contiguous block, and pass 1 shards with it) or both:
+ * out fp32 (C, x1-x0, H, z1-z0).  For REFNTF/LEGACY the output grid equals the low-res grid.
  *   class_offsets int32 (C+1) prefix offsets into the A prototypes.                        */
 int vittf_sim_upsample(const float* dots, const float* gram, int w, int h, int d, int A, const int* class_offsets,
-                       int C, int W, int H, int D, int z0, int z1, int mode, float threshold, float exponent,
+                       int C, int W, int H, int D, int x0, int x1, int z0, int z1, int mode, float threshold, float exponent,
                        int dots_layout, float* out, void* stream);
 
 /* 0.99*max quantisation input (predict_ntf.py:95): per-class maximum, out fp32 (C) */

@@ -106,6 +106,15 @@ def test_ns_similarity_matches_oracle(lr, out_shape, F_, A):
     zs = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
                          out_shape, mode="ns", exponent=2.0, z_range=(3, out_shape[2] - 2)).cpu()
     assert torch.equal(zs, out[..., 3:out_shape[2] - 2])
+    # x-slab evaluation (the slowest axis: pass 1 only evaluates the low-res planes under the slab +- 1)
+    if out_shape[0] >= 8:
+        xa, xb = out_shape[0] // 4, out_shape[0] - 3
+        xs = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
+                             out_shape, mode="ns", exponent=2.0, x_range=(xa, xb)).cpu()
+        assert torch.equal(xs, out[:, xa:xb])
+        xz = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
+                             out_shape, mode="ns", exponent=2.0, x_range=(0, xa + 1), z_range=(3, out_shape[2] - 2)).cpu()
+        assert torch.equal(xz, out[:, :xa + 1, :, 3:out_shape[2] - 2])
     if out_shape[2] >= 16:                                        # even slab bounds: the vectorised store path
         zs = similarity_maps(feats.cuda(), p.cuda().contiguous(), torch.tensor(offs, dtype=torch.int32, device="cuda"),
                              out_shape, mode="ns", exponent=2.5, z_range=(4, out_shape[2] - 6)).cpu()
@@ -151,6 +160,12 @@ def test_ns_similarity_full_size(F_, n, N, A, C):
         zs = similarity_maps(fc, pc, oc, (N, N, N), mode="ns", exponent=2.0, z_range=(z0, z1))
         assert torch.equal(zs, out[..., z0:z1])
     del zs
+    # x-slab sharding (similarity-only workloads: pass 1 shards with the maps): 3 uneven slabs, bit-exact
+    cuts = [0, N // 4 + 2, N // 2 + 8, N]
+    for x0, x1 in zip(cuts[:-1], cuts[1:]):
+        xs = similarity_maps(fc, pc, oc, (N, N, N), mode="ns", exponent=2.0, x_range=(x0, x1))
+        assert torch.equal(xs, out[:, x0:x1])
+    del xs
     # prototype order inside a class
     perm = torch.cat([torch.arange(offs[c], offs[c + 1]).flip(0) for c in range(C)])
     out2 = similarity_maps(fc, pc[perm.cuda()].contiguous(), oc, (N, N, N), mode="ns", exponent=2.0)

@@ -63,8 +63,8 @@ _SIGNATURES = {
     "vittf_patch_embed": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "vittf_sample_prototypes": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _p]),
     "vittf_sim_lowres_layout": (_i, [_i, _i, _i, _i, _i, _p]),
-    "vittf_sim_lowres": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p]),
-    "vittf_sim_upsample": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p]),
+    "vittf_sim_lowres": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
+    "vittf_sim_upsample": (_i, [_p, _p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p]),
     "vittf_class_max": (_i, [_p, _i, _i64, _p, _p]),
     "vittf_quantize_maps_u8": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "vittf_labels": (_i, [_p, _i, _i, _i64, _p, _i, _p, _p]),

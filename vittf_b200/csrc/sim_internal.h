@@ -8,9 +8,10 @@ struct UpParams {
     const float* dots;           // (A, n_lr)
     const float* gram;           // (14, n_lr) or nullptr
     const int* class_offsets;    // (C + 1), device
-    float* out;                  // (C, W, H, z1 - z0)
+    float* out;                  // (C, x1 - x0, H, z1 - z0)
     int w, h, d, A, C;
     int W, H, D, z0, z1;
+    int x0, x1;                  // output x-slab [x0, x1) (slab sharding along the slowest axis); out is (C, x1 - x0, H, z1 - z0)
     int mode;
     float threshold, exponent;
 };

@@ -69,6 +69,8 @@ struct TcParams {
     float* out;
     int w, h, d, A, C;
     int W, H, D, z0, z1;
+    int x0, x1;        // output x-slab
+    int xrow0;         // U = 2, 4: first x cell (cx) of the slab
     float exponent;
     int nz;            // rows along z per (x, y): z chunks (U = 2, 4) or z cells (U = 8) overlapping the slab
     int zrow0;         // first z chunk / z cell
@@ -121,8 +123,9 @@ __device__ __forceinline__ float pow_sat(float x, float e) {      // x already i
 template <int U>
 __device__ __forceinline__ bool decode_row(const TcParams& p, int tile, int r, int& ix, int& iy, int& iz) {
     if (U == 8) {
-        ix = tile / p.tiles_per_x;
-        const int rr = (tile - ix * p.tiles_per_x) * 128 + r;
+        const int xi = tile / p.tiles_per_x;
+        ix = p.x0 + xi;                                   // output x plane
+        const int rr = (tile - xi * p.tiles_per_x) * 128 + r;
         const bool live = rr < p.rows_per_x;
         const int rc = live ? rr : p.rows_per_x - 1;
         iy = rc / p.nz;
@@ -133,8 +136,9 @@ __device__ __forceinline__ bool decode_row(const TcParams& p, int tile, int r, i
         const bool live = rr < p.n_rows;
         rr = live ? rr : p.n_rows - 1;
         const int per_x = (p.h + 1) * p.nz;
-        ix = static_cast<int>(rr / per_x);
-        const int rem = static_cast<int>(rr - static_cast<int64_t>(ix) * per_x);
+        const int xi = static_cast<int>(rr / per_x);
+        ix = p.xrow0 + xi + 1;                            // cell cx + 1
+        const int rem = static_cast<int>(rr - static_cast<int64_t>(xi) * per_x);
         iy = rem / p.nz;
         iz = p.zrow0 + (rem - iy * p.nz);
         return live;
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sim_upsample_tc_kernel(TcParams
             const uint64_t b_desc0 = ptx::smem_desc_k_sw128(ptx::smem_u32(s_b));
             uint32_t g = 0, gs = 0;                                  // prototypes / operand stages (pairs) issued so far
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int sub = U == 8 ? ((tile / p.tiles_per_x + 4) & 7) : 0;         // kx of the tile's output x plane
+                const int sub = U == 8 ? ((p.x0 + tile / p.tiles_per_x + 4) & 7) : 0;  // kx of the tile's output x plane
                 const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(sub * (B_BYTES >> 4));
                 for (int a = 0; a < p.A; a += 2, ++gs) {
                     const uint32_t st = gs % TC_STAGES;
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sim_upsample_tc_kernel(TcParams
         const int r = threadIdx.x & 127;
         const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const uint32_t col0 = half * CW;
-        const int64_t n_out = static_cast<int64_t>(p.W) * p.H * zs;
+        const int64_t n_out = static_cast<int64_t>(p.x1 - p.x0) * p.H * zs;
         uint32_t g = 0, tn = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tn) {
             int ix, iy, iz;
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sim_upsample_tc_kernel(TcParams
             const int oz0 = U == 8 ? 8 * iz + 4 : 4 * iz;
             uint32_t xmask = 0, ymask = 0, zmask = 0;
 #pragma unroll
-            for (int k = 0; k < BX; ++k) xmask |= (ox0 + k >= 0 && ox0 + k < p.W) ? (1u << k) : 0u;
+            for (int k = 0; k < BX; ++k) xmask |= (ox0 + k >= p.x0 && ox0 + k < p.x1) ? (1u << k) : 0u;
 #pragma unroll
             for (int k = 0; k < BY; ++k) ymask |= (oy0 + k >= 0 && oy0 + k < p.H) ? (1u << k) : 0u;
 #pragma unroll
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sim_upsample_tc_kernel(TcParams
                 const int run = half * RUNS + q;               // `half` is warp-uniform, q compile-time
                 runmask |= (((xmask >> (run / BY)) & 1u) & ((ymask >> (run % BY)) & 1u)) << q;
             }
-            const int64_t obase = (static_cast<int64_t>(ox0 + (half * RUNS) / BY) * p.H + oy0 + (half * RUNS) % BY) * zs + (oz0 - p.z0);
+            const int64_t obase = (static_cast<int64_t>(ox0 - p.x0 + (half * RUNS) / BY) * p.H + oy0 + (half * RUNS) % BY) * zs + (oz0 - p.z0);
 
             float cls[CW];
 #pragma unroll
@@ -657,6 +661,7 @@ int launch_tc_u(const UpParams& q, cudaStream_t s) {
     p.dots = q.dots; p.gram = q.gram; p.class_offsets = q.class_offsets; p.out = q.out;
     p.w = q.w; p.h = q.h; p.d = q.d; p.A = q.A; p.C = q.C;
     p.W = q.W; p.H = q.H; p.D = q.D; p.z0 = q.z0; p.z1 = q.z1;
+    p.x0 = q.x0; p.x1 = q.x1;
     p.exponent = q.exponent;
     p.A4 = (q.A + 3) & ~3;
     auto fdiv = [](int a, int b) { return (a >= 0 ? a : a - b + 1) / b; };
@@ -668,11 +673,13 @@ int launch_tc_u(const UpParams& q, cudaStream_t s) {
         p.nz = c_hi - c_lo + 1;
         p.rows_per_x = (q.h + 1) * p.nz;
         p.tiles_per_x = (p.rows_per_x + 127) / 128;
-        tiles = static_cast<int64_t>(q.W) * p.tiles_per_x;
+        tiles = static_cast<int64_t>(q.x1 - q.x0) * p.tiles_per_x;
     } else {
         p.zrow0 = q.z0 / 4;
         p.nz = (q.z1 + 3) / 4 - p.zrow0;
-        p.n_rows = static_cast<int64_t>(q.w + 1) * (q.h + 1) * p.nz;
+        const int cx_lo = fdiv(q.x0 - U / 2, U), cx_hi = fdiv(q.x1 - 1 - U / 2, U);    // x cells -1 .. w-1 overlapping the slab
+        p.xrow0 = cx_lo;
+        p.n_rows = static_cast<int64_t>(cx_hi - cx_lo + 1) * (q.h + 1) * p.nz;
         tiles = (p.n_rows + 127) / 128;
     }
     if (tiles <= 0 || tiles > 0x7fffffff) return -1;

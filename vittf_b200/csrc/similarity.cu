@@ -182,7 +182,7 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
 template <int NT>   // N-tiles of 8 prototypes handled by the CTA (A <= 8 * NT)
 __global__ void __launch_bounds__(128) sim_dots_mma_kernel(const __grid_constant__ CUtensorMap tm_f, int F, int64_t n,
                                                            const float* __restrict__ protos, int A, int a_base,
-                                                           float* __restrict__ dots, int64_t sa, int64_t sv) {
+                                                           float* __restrict__ dots, int64_t sa, int64_t sv, int64_t v_first) {
     extern __shared__ __align__(1024) uint8_t dm_smem_raw[];
     uint8_t* dm_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dm_smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_t = dm_smem;                                                   // [stage][box][32 f][64 v] halves, swizzled
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(128) sim_dots_mma_kernel(const __grid_constant
     const int pstride = F + 8;
     uint64_t* full = reinterpret_cast<uint64_t*>(s_p + static_cast<size_t>(8 * NT) * pstride);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int64_t v0 = static_cast<int64_t>(blockIdx.x) * DM_BM;
+    const int64_t v0 = v_first + static_cast<int64_t>(blockIdx.x) * DM_BM;      // n = end of the voxel range
     const int nchunk = (F + DM_BK - 1) / DM_BK;
     if (tid == 0) {
         for (int i = 0; i < DM_STAGES; ++i) ptx::mbar_init(&full[i], 1);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(128) sim_dots_mma_kernel(const __grid_constant
 
 template <int NT>
 int launch_dots_mma_one(const CUtensorMap& tm, int F, int64_t n, const float* protos, int A, int a_base, float* dots,
-                        int64_t sa, int64_t sv, cudaStream_t s) {
+                        int64_t sa, int64_t sv, int64_t v_first, cudaStream_t s) {
     const size_t smem = static_cast<size_t>(DM_STAGES) * DM_STAGE_BYTES + static_cast<size_t>(8 * NT) * (F + 8) * 2 + 64 + 1024;
     auto kern = sim_dots_mma_kernel<NT>;
     static PerDeviceMemo configured;
@@ -282,15 +282,16 @@ int launch_dots_mma_one(const CUtensorMap& tm, int F, int64_t n, const float* pr
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured.cur() = smem;
     }
-    kern<<<static_cast<unsigned>(ceil_div_ll(n, DM_BM)), 128, smem, s>>>(tm, F, n, protos, A, a_base, dots, sa, sv);
+    kern<<<static_cast<unsigned>(ceil_div_ll(n - v_first, DM_BM)), 128, smem, s>>>(tm, F, n, protos, A, a_base, dots, sa, sv, v_first);
     vittf_count_launches(1);
     return VITTF_OK;
 }
 
 // all prototypes, 64 per launch
 int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, int A, float* dots, cudaStream_t s, int a_first = 0,
-                    int64_t sa = -1, int64_t sv = 1) {
+                    int64_t sa = -1, int64_t sv = 1, int64_t v_first = 0, int64_t v_end = -1) {
     if (sa < 0) sa = n;
+    if (v_end < 0) v_end = n;
     CUtensorMap tm;
     const uint64_t dims[2] = {static_cast<uint64_t>(n), static_cast<uint64_t>(F)};
     const uint64_t strides[1] = {static_cast<uint64_t>(n) * 2};
@@ -299,10 +300,10 @@ int launch_dots_mma(const __half* feats, int F, int64_t n, const float* protos, 
     for (int a_base = a_first; a_base < A; a_base += 64) {
         const int rem = A - a_base;
         int rc;
-        if (rem > 32) rc = launch_dots_mma_one<8>(tm, F, n, protos, A, a_base, dots, sa, sv, s);
-        else if (rem > 16) rc = launch_dots_mma_one<4>(tm, F, n, protos, A, a_base, dots, sa, sv, s);
-        else if (rem > 8) rc = launch_dots_mma_one<2>(tm, F, n, protos, A, a_base, dots, sa, sv, s);
-        else rc = launch_dots_mma_one<1>(tm, F, n, protos, A, a_base, dots, sa, sv, s);
+        if (rem > 32) rc = launch_dots_mma_one<8>(tm, F, v_end, protos, A, a_base, dots, sa, sv, v_first, s);
+        else if (rem > 16) rc = launch_dots_mma_one<4>(tm, F, v_end, protos, A, a_base, dots, sa, sv, v_first, s);
+        else if (rem > 8) rc = launch_dots_mma_one<2>(tm, F, v_end, protos, A, a_base, dots, sa, sv, v_first, s);
+        else rc = launch_dots_mma_one<1>(tm, F, v_end, protos, A, a_base, dots, sa, sv, v_first, s);
         VITTF_CHECK(rc);
     }
     VITTF_CHECK_CUDA(cudaGetLastError());
@@ -337,7 +338,7 @@ template <int NT>   // n-tiles of 8 prototypes (A <= 8 * NT)
 __global__ void __maxnreg__(168)
     sim_lowres_mma_kernel(const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm1, int F, int w, int h, int d,
                           const float* __restrict__ protos, int A, float* __restrict__ dots, float* __restrict__ gram,
-                          int tiles_y, int tiles_z, int ntiles, int nstages, int64_t sa, int64_t sv) {
+                          int tiles_y, int tiles_z, int ntiles, int nstages, int64_t sa, int64_t sv, int xa) {
     extern __shared__ __align__(1024) uint8_t gm_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gm_raw) + 127) & ~uintptr_t(127));
     uint8_t* s_t = smem;                                                                   // [stage][X | P | Q]
@@ -378,7 +379,7 @@ __global__ void __maxnreg__(168)
             uint32_t ph = 0;                                  // parity of the phase that releases the stage's previous use
             bool first_round = true;                          // (nothing to wait for while the ring fills for the first time)
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int zb = tile % tiles_z, yb = (tile / tiles_z) % tiles_y, x = tile / (tiles_z * tiles_y);
+                const int zb = tile % tiles_z, yb = (tile / tiles_z) % tiles_y, x = xa + tile / (tiles_z * tiles_y);
                 const int tz = zb * GM_TZ - 8, y0 = yb * 2;
                 for (int c = 0; c < nchunk; ++c) {
                     if (!first_round) ptx::mbar_wait_quiet(&empty[st], ph);
@@ -481,7 +482,7 @@ __global__ void __maxnreg__(168)
             }
         }
         // ---- tile epilogue: the wanted diagonals of the accumulators -> gram planes, prototype columns -> dots --------
-        const int zb = tile % tiles_z, yb = (tile / tiles_z) % tiles_y, x = tile / (tiles_z * tiles_y);
+        const int zb = tile % tiles_z, yb = (tile / tiles_z) % tiles_y, x = xa + tile / (tiles_z * tiles_y);
         const int y = yb * 2 + li, z0 = zb * GM_TZ + 16 * zt;
         const bool yok = y < h;
         const int64_t vb = (static_cast<int64_t>(x) * h + y) * d + z0;
@@ -519,9 +520,9 @@ __global__ void __maxnreg__(168)
 
 template <int NT>
 int launch_lowres_mma_one(const CUtensorMap& tm3, const CUtensorMap& tm1, int F, int w, int h, int d, const float* protos, int A,
-                          float* dots, float* gram, int64_t sa, int64_t sv, cudaStream_t s) {
+                          float* dots, float* gram, int64_t sa, int64_t sv, int xa, int xb, cudaStream_t s) {
     const int tiles_z = ceil_div(d, GM_TZ), tiles_y = ceil_div(h, 2);
-    const int ntiles = tiles_z * tiles_y * w;
+    const int ntiles = tiles_z * tiles_y * (xb - xa);
     const size_t panel = static_cast<size_t>(8 * NT) * (F + 8) * 2;
     int nstages = static_cast<int>((220 * 1024 - panel - 256) / GM_STAGE);
     nstages = nstages > 8 ? 8 : nstages;
@@ -534,14 +535,15 @@ int launch_lowres_mma_one(const CUtensorMap& tm3, const CUtensorMap& tm1, int F,
         configured.cur() = smem;
     }
     const int grid = ntiles < vittf_num_sms() ? ntiles : vittf_num_sms();
-    kern<<<grid, 32 * (GM_CONSUMERS + 1), smem, s>>>(tm3, tm1, F, w, h, d, protos, A, dots, gram, tiles_y, tiles_z, ntiles, nstages, sa, sv);
+    kern<<<grid, 32 * (GM_CONSUMERS + 1), smem, s>>>(tm3, tm1, F, w, h, d, protos, A, dots, gram, tiles_y, tiles_z, ntiles, nstages, sa, sv, xa);
     vittf_count_launches(1);
     return VITTF_OK;
 }
 
 // first <= 32 prototypes + Gram planes fused; prototypes beyond 32 on the dots-only tensor-core kernel
 int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const float* protos, int A, float* dots, float* gram,
-                      cudaStream_t s, int layout = 0) {
+                      cudaStream_t s, int layout = 0, int xa = 0, int xb = -1) {
+    if (xb < 0) xb = w;
     // layout 0: dots (A, n_lr); 1: (n_lr, A4) with A4 = A rounded up to 4 (the tcgen05 up-sampling kernel gathers the corner
     // dots of 4 prototypes with one 16-byte load)
     const int64_t n_lr = static_cast<int64_t>(w) * h * d;
@@ -554,11 +556,11 @@ int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const flo
     VITTF_CHECK(vittf_make_tmap(&tm1, feats, 2, 4, dims, strides, box1, false));
     const int a0 = A < 32 ? A : 32;
     int rc;
-    if (a0 > 16) rc = launch_lowres_mma_one<4>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, s);
-    else if (a0 > 8) rc = launch_lowres_mma_one<2>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, s);
-    else rc = launch_lowres_mma_one<1>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, s);
+    if (a0 > 16) rc = launch_lowres_mma_one<4>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, xa, xb, s);
+    else if (a0 > 8) rc = launch_lowres_mma_one<2>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, xa, xb, s);
+    else rc = launch_lowres_mma_one<1>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, xa, xb, s);
     if (rc != VITTF_OK) return rc;
-    if (A > 32) VITTF_CHECK(launch_dots_mma(feats, F, n_lr, protos, A, dots, s, 32, sa, sv));
+    if (A > 32) VITTF_CHECK(launch_dots_mma(feats, F, n_lr, protos, A, dots, s, 32, sa, sv, static_cast<int64_t>(xa) * h * d, static_cast<int64_t>(xb) * h * d));
     VITTF_CHECK_CUDA(cudaGetLastError());
     return VITTF_OK;
 }
@@ -590,12 +592,12 @@ __global__ void __launch_bounds__(256) sim_upsample_kernel(UpParams q) {
     for (int i = threadIdx.x; i <= q.C; i += blockDim.x) s_off[i] = q.class_offsets[i];
     __syncthreads();
     const int zs = q.z1 - q.z0;
-    const int64_t n_out = static_cast<int64_t>(q.W) * q.H * zs;
+    const int64_t n_out = static_cast<int64_t>(q.x1 - q.x0) * q.H * zs;
     const int64_t n_lr = static_cast<int64_t>(q.w) * q.h * q.d;
     for (int64_t o = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; o < n_out;
          o += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int oz = static_cast<int>(o % zs), oy = static_cast<int>((o / zs) % q.H),
-                  ox = static_cast<int>(o / (static_cast<int64_t>(zs) * q.H));
+                  ox = q.x0 + static_cast<int>(o / (static_cast<int64_t>(zs) * q.H));
         int x0, x1, y0, y1, c0, c1;
         float tx, ty, tz;
         src_index(ox, q.w, q.W, x0, x1, tx);
@@ -717,7 +719,7 @@ __device__ __forceinline__ uint32_t bit_range(int lo, int hi) {
 constexpr int UP_PD = 4;            // prefetch distance of the corner dots, in prototypes
 
 template <int U, int EXPK>
-__global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, int cz_lo, int ncz, int tiles_per_x, int total_tasks) {
+__global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, int cz_lo, int ncz, int tiles_per_x, int total_tasks, int cx_lo) {
     constexpr int NSUB = U == 8 ? 8 : 1;             // sub-blocks of 64 outputs per cell
     extern __shared__ __align__(16) uint8_t um_smem[];
     int* s_off = reinterpret_cast<int*>(um_smem);
@@ -735,7 +737,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
     const int task = static_cast<int>(blockIdx.x) * 4 + warp;
     if (task >= total_tasks) return;
     const int cxi = task / tiles_per_x, tile = task - cxi * tiles_per_x;
-    const int cx = cxi - 1;
+    const int cx = cx_lo + cxi;
     const int w = q.w, h = q.h, d = q.d;
     const int ncells = (h + 1) * ncz;
     const uint32_t n_lr = static_cast<uint32_t>(w) * h * d;
@@ -768,7 +770,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
         zok[r][0] = rlive && oz >= q.z0 && oz < q.z1 && oz >= 0 && oz < q.D;
         zok[r][1] = rlive && oz + 1 >= q.z0 && oz + 1 < q.z1 && oz + 1 >= 0 && oz + 1 < q.D;
         oyb[r] = U * cy + U / 2 + ky_t;
-        obase[r] = (oxb * q.H + oyb[r]) * zs + (oz - q.z0);
+        obase[r] = ((oxb - q.x0) * q.H + oyb[r]) * zs + (oz - q.z0);
         ycl[r][0] = y0c;
         ycl[r][1] = y1c;
         zcl[r][0] = z0c;
@@ -845,7 +847,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
     }
     const bool vec_ok = (q.z0 & 1) == 0 && (zs & 1) == 0 && (reinterpret_cast<uintptr_t>(q.out) & 7) == 0;
     const int Hzs = q.H * zs;
-    const size_t n_out = static_cast<size_t>(q.W) * Hzs;
+    const size_t n_out = static_cast<size_t>(q.x1 - q.x0) * Hzs;
 
     uint32_t whi[8], wlo[8];
     if (U == 4) {
@@ -863,7 +865,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
     for (int r = 0; r < 2; ++r) {
         uint32_t mr;
         if (U == 4) {
-            const uint32_t mx = bit_range(-oxb, q.W - oxb);                       // bit kx
+            const uint32_t mx = bit_range(q.x0 - oxb, q.x1 - oxb);                // bit kx
             const uint32_t mx2 = ((mx & 1) * 3u) | (((mx >> 1) & 1) * 12u) | (((mx >> 2) & 1) * 48u) | (((mx >> 3) & 1) * 192u);
             const uint32_t my = ((oyb[r] >= 0 && oyb[r] < q.H) ? 0x55u : 0u) | ((oyb[r] + 2 >= 0 && oyb[r] + 2 < q.H) ? 0xaau : 0u);
             mr = mx2 & my;
@@ -886,7 +888,7 @@ __global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, in
                 whi[j] = f.x;
                 wlo[j] = f.y;
             }
-            const bool xok = oxb + sub >= 0 && oxb + sub < q.W;
+            const bool xok = oxb + sub >= q.x0 && oxb + sub < q.x1;
             ms0 = xok ? m0 : 0u;
             ms1 = xok ? m1 : 0u;
         }
@@ -1026,15 +1028,16 @@ int launch_upsample_mma(const UpParams& q, cudaStream_t s) {
     const int cz_lo = fdiv(q.z0 - U / 2, U), cz_hi = fdiv(q.z1 - 1 - U / 2, U);
     const int ncz = cz_hi - cz_lo + 1;
     const int tiles_per_x = ceil_div((q.h + 1) * ncz, 16);
-    const long long total = static_cast<long long>(q.w + 1) * tiles_per_x;
+    const int cx_lo = fdiv(q.x0 - U / 2, U), cx_hi = fdiv(q.x1 - 1 - U / 2, U);      // x cells overlapping the slab
+    const long long total = static_cast<long long>(cx_hi - cx_lo + 1) * tiles_per_x;
     if (total > 0x7fffffff / 4) return -1;
     const size_t smem = (((q.C + 1) * 4 + 15) & ~15) + (U == 8 ? 64 : 8) * 32 * sizeof(uint2);
     const unsigned grid = static_cast<unsigned>((total + 3) / 4);
     const int tt = static_cast<int>(total);
-    if (q.exponent == 2.0f) sim_upsample_mma_kernel<U, 0><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt);
-    else if (q.exponent == 2.5f) sim_upsample_mma_kernel<U, 1><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt);
-    else if (q.exponent == 1.0f) sim_upsample_mma_kernel<U, 2><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt);
-    else sim_upsample_mma_kernel<U, 3><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt);
+    if (q.exponent == 2.0f) sim_upsample_mma_kernel<U, 0><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt, cx_lo);
+    else if (q.exponent == 2.5f) sim_upsample_mma_kernel<U, 1><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt, cx_lo);
+    else if (q.exponent == 1.0f) sim_upsample_mma_kernel<U, 2><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt, cx_lo);
+    else sim_upsample_mma_kernel<U, 3><<<grid, 128, smem, s>>>(q, cz_lo, ncz, tiles_per_x, tt, cx_lo);
     return 0;
 }
 
@@ -1170,16 +1173,17 @@ extern "C" int vittf_sim_lowres_layout(int feat_dtype, int F, int w, int h, int 
 }
 
 extern "C" int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w, int h, int d, const float* protos, int A,
-                                float* dots, float* gram, int dots_layout, void* stream) {
+                                float* dots, float* gram, int dots_layout, int xa, int xb, void* stream) {
     VITTF_REQUIRE(feats && protos && dots, "vittf_sim_lowres: null pointer");
     VITTF_REQUIRE(F > 0 && w > 0 && h > 0 && d > 0 && A > 0, "vittf_sim_lowres: empty problem");
+    VITTF_REQUIRE(xa >= 0 && xb > xa && xb <= w, "vittf_sim_lowres: x-plane range [%d,%d) outside [0,%d)", xa, xb, w);
     const bool fused = vittf_sim_lowres_layout(feat_dtype, F, w, h, d, feats) != 0;
     VITTF_REQUIRE(dots_layout == 0 || (dots_layout == 1 && fused),
                   "vittf_sim_lowres: dots_layout %d is not available for this input (ask vittf_sim_lowres_layout)", dots_layout);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (fused) {
         // fp16 features, F % 32 == 0, d % 8 == 0: dots + Gram from one read of the volume on the tensor cores
-        const int rc = launch_lowres_mma(static_cast<const __half*>(feats), F, w, h, d, protos, A, dots, gram, s, dots_layout);
+        const int rc = launch_lowres_mma(static_cast<const __half*>(feats), F, w, h, d, protos, A, dots, gram, s, dots_layout, xa, xb);
         if (rc != -1) return rc;
         VITTF_REQUIRE(dots_layout == 0, "vittf_sim_lowres: fused pass unavailable for F=%d", F);
     }
@@ -1197,16 +1201,16 @@ extern "C" int vittf_sim_lowres(const void* feats, int feat_dtype, int F, int w,
 }
 
 extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, int h, int d, int A,
-                                  const int* class_offsets, int C, int W, int H, int D, int z0, int z1, int mode,
+                                  const int* class_offsets, int C, int W, int H, int D, int x0, int x1, int z0, int z1, int mode,
                                   float threshold, float exponent, int dots_layout, float* out, void* stream) {
     VITTF_REQUIRE(dots && class_offsets && out, "vittf_sim_upsample: null pointer");
     VITTF_REQUIRE(dots_layout == 0 || dots_layout == 1, "vittf_sim_upsample: dots_layout must be 0 (A, n_lr) or 1 (n_lr, A4)");
     VITTF_REQUIRE(mode == VITTF_SIM_NS || mode == VITTF_SIM_REFNTF || mode == VITTF_SIM_LEGACY || mode == VITTF_SIM_CLAMP_MEAN,
                   "vittf_sim_upsample: unknown mode %d", mode);
     VITTF_REQUIRE(mode == VITTF_SIM_REFNTF || mode == VITTF_SIM_CLAMP_MEAN || gram, "vittf_sim_upsample: NS/LEGACY modes need the Gram planes");
-    VITTF_REQUIRE(C > 0 && A > 0 && W > 0 && H > 0 && D > 0 && z0 >= 0 && z1 > z0 && z1 <= D,
-                  "vittf_sim_upsample: bad sizes (C=%d A=%d out=%dx%dx%d z=[%d,%d))", C, A, W, H, D, z0, z1);
-    UpParams q{dots, gram, class_offsets, out, w, h, d, A, C, W, H, D, z0, z1, mode, threshold, exponent};
+    VITTF_REQUIRE(C > 0 && A > 0 && W > 0 && H > 0 && D > 0 && z0 >= 0 && z1 > z0 && z1 <= D && x0 >= 0 && x1 > x0 && x1 <= W,
+                  "vittf_sim_upsample: bad sizes (C=%d A=%d out=%dx%dx%d x=[%d,%d) z=[%d,%d))", C, A, W, H, D, x0, x1, z0, z1);
+    UpParams q{dots, gram, class_offsets, out, w, h, d, A, C, W, H, D, z0, z1, x0, x1, mode, threshold, exponent};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dots_layout == 1) {
         // voxel-major dots: NS mode with one integer factor 2 / 4 / 8 on the tcgen05 cell-tile kernel (sim_up_tc.cu)
@@ -1219,7 +1223,7 @@ extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, i
     // NS mode, one factor 4 or 8 on all three axes: warp-level mma.sync cell-tile kernel (cheaper per prototype than the
     // tcgen05 kernel: no TMEM round trip per prototype -- profiles/r2_sim_kernels.md)
     if (!sim_generic_only() && mode == VITTF_SIM_NS && (W == 4 * w || W == 8 * w) && H * static_cast<int64_t>(w) == static_cast<int64_t>(h) * W &&
-        D * static_cast<int64_t>(w) == static_cast<int64_t>(d) * W && static_cast<int64_t>(W) * H * (z1 - z0) < (1ll << 30) &&
+        D * static_cast<int64_t>(w) == static_cast<int64_t>(d) * W && static_cast<int64_t>(x1 - x0) * H * (z1 - z0) < (1ll << 30) &&
         static_cast<int64_t>(w) * h * d < (1ll << 31)) {
         const int rc = W == 4 * w ? launch_upsample_mma<4>(q, s) : launch_upsample_mma<8>(q, s);
         if (rc == 0) {
@@ -1229,7 +1233,7 @@ extern "C" int vittf_sim_upsample(const float* dots, const float* gram, int w, i
         }
     }
     // every other scale factor, mode and shape
-    const int64_t n_out = static_cast<int64_t>(W) * H * (z1 - z0);
+    const int64_t n_out = static_cast<int64_t>(x1 - x0) * H * (z1 - z0);
     int64_t blocks = ceil_div_ll(n_out, 256);
     const int64_t cap = static_cast<int64_t>(vittf_num_sms()) * 32;
     if (blocks > cap) blocks = cap;

@@ -34,6 +34,12 @@ def z_range(depth, world, rank):
     return depth * rank // world, depth * (rank + 1) // world
 
 
+def x_range(width, world, rank):
+    """Output x-slab [x0, x1) of `rank`: the similarity-only workloads shard along the slowest axis, so that pass 1
+    (dots + Gram over the low-res planes under the slab +- 1) shards with the maps."""
+    return width * rank // world, width * (rank + 1) // world
+
+
 def all_reduce_disjoint(buf, group=None):
     """Sum of per-rank buffers with disjoint supports (exact, see module docstring)."""
     import torch.distributed as dist

@@ -171,9 +171,10 @@ def sample_prototypes(feats, rel, mode):
 
 
 @_on_device
-def sim_lowres(feats, protos, want_gram=True, voxel_major=False):
+def sim_lowres(feats, protos, want_gram=True, voxel_major=False, x_planes=None):
     """Pass 1: dots fp32 (A, n_lr) -- or (n_lr, A4), A4 = A rounded up to 4, with voxel_major=True where the fused
-    tensor-core pass is available (else the flag is ignored) -- and the 14 Gram planes.  Returns (dots, gram, layout)."""
+    tensor-core pass is available (else the flag is ignored) -- and the 14 Gram planes.  x_planes=(xa, xb) restricts
+    the evaluation to those low-res x planes (slab sharding).  Returns (dots, gram, layout)."""
     require_cuda(feats, protos)
     F, w, h, d = feats.shape
     A = protos.shape[0]
@@ -183,23 +184,25 @@ def sim_lowres(feats, protos, want_gram=True, voxel_major=False):
         layout = int(load().vittf_sim_lowres_layout(DTYPE_CODE[feats.dtype], F, w, h, d, ptr(feats)))
     dots = torch.empty((n, (A + 3) // 4 * 4) if layout else (A, n), dtype=torch.float32, device=feats.device)
     gram = torch.empty(14, n, dtype=torch.float32, device=feats.device) if want_gram else None
+    xa, xb = (0, w) if x_planes is None else x_planes
     check(load().vittf_sim_lowres(ptr(feats), DTYPE_CODE[feats.dtype], F, w, h, d, ptr(protos), A, ptr(dots), ptr(gram), layout,
-                                  stream_ptr(feats.device)), "vittf_sim_lowres")
+                                  int(xa), int(xb), stream_ptr(feats.device)), "vittf_sim_lowres")
     return dots, gram, layout
 
 
 @_on_device
 def sim_upsample(dots, gram, lr_shape, class_offsets, out_shape, mode, threshold=0.25, exponent=2.0, z0=0, z1=None, out=None,
-                 layout=0, n_protos=None):
+                 layout=0, n_protos=None, x0=0, x1=None):
     require_cuda(dots, gram, class_offsets, out)
     w, h, d = lr_shape
     W, H, D = out_shape
     z1 = D if z1 is None else z1
+    x1 = W if x1 is None else x1
     C_ = class_offsets.numel() - 1
     A = n_protos if n_protos is not None else (dots.shape[0] if layout == 0 else dots.shape[1])
     if out is None:
-        out = torch.empty(C_, W, H, z1 - z0, dtype=torch.float32, device=dots.device)
-    check(load().vittf_sim_upsample(ptr(dots), ptr(gram), w, h, d, A, ptr(class_offsets), C_, W, H, D, z0, z1,
+        out = torch.empty(C_, x1 - x0, H, z1 - z0, dtype=torch.float32, device=dots.device)
+    check(load().vittf_sim_upsample(ptr(dots), ptr(gram), w, h, d, A, ptr(class_offsets), C_, W, H, D, x0, x1, z0, z1,
                                     mode, float(threshold), float(exponent), int(layout), ptr(out), stream_ptr(dots.device)),
           "vittf_sim_upsample")
     return out
