@@ -70,6 +70,11 @@ typedef struct {
     const float* ln2_w; const float* ln2_b;
     const void* fc1_w;  const float* fc1_b;   /* (4D, D) */
     const void* fc2_w;  const float* fc2_b;   /* (D, 4D) */
+    /* LayerNorm folded into the projections that follow it (vittf_gemm_bf16_ln).  Both NULL: qkv_w / fc1_w are the plain
+     * weights and norm1 / norm2 run as vittf_layernorm.  Both set: qkv_w = bf16(W_qkv * ln1_w), qkv_b = b + W_qkv ln1_b,
+     * qkv_colsum fp32 (3D) = row sums of that bf16 matrix; likewise fc1_* with ln2_*; ln*_w / ln*_b are then unused. */
+    const float* qkv_colsum;
+    const float* fc1_colsum;
 } vittf_block_weights;
 
 typedef struct vittf_vit vittf_vit; /* opaque */
@@ -124,7 +129,7 @@ int vittf_accumulate_f16(void* out_f16, const void* in_f16, int64_t n, void* str
 
 /* -------- individually exported building blocks (unit-tested against torch) ---------- */
 enum { VITTF_EPI_BIAS_BF16 = 0, VITTF_EPI_BIAS_GELU_BF16 = 1, VITTF_EPI_BIAS_RESID_F32 = 2,
-       VITTF_EPI_QKV_SPLIT = 3, VITTF_EPI_KFEAT_F16 = 4 };
+       VITTF_EPI_QKV_SPLIT = 3, VITTF_EPI_KFEAT_F16 = 4, VITTF_EPI_BIAS_RESID_LN = 5 };
 /* C[M,N] = A[M,K] (bf16, row-major) x W[N,K]^T (bf16) + bias, tcgen05/TMEM/TMA.
  *   epi 0/1: out bf16 (M,N) [GELU(erf) for 1];  epi 2: out fp32 (M,N) += (residual stream);
  *   epi 3: N = 3D, out = qk bf16 (M, 2D), out2 = V^T bf16 (B*heads*64, tok_pad) with
@@ -132,6 +137,32 @@ enum { VITTF_EPI_BIAS_BF16 = 0, VITTF_EPI_BIAS_GELU_BF16 = 1, VITTF_EPI_BIAS_RES
  *   epi 4: out fp16 ((M/tokens)*(tokens-1), N): CLS rows dropped (K features).             */
 int vittf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, void* out2, int M, int N, int K,
                     int epi, int tokens, int tok_pad, void* stream);
+/* The same GEMM with the LayerNorm of the pre-LN blocks (hub Block.forward: x + attn(norm1(x)), x + mlp(norm2(x)),
+ * called from infer.py:177) folded into the linear layers around it, so that no LayerNorm pass runs:
+ *   LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * colsum(W*gamma)) + (b + W beta).
+ * The fp32 residual stream lives in a ROW-TILED layout xt[m_pad/32][D/4][32 rows][4 columns] (m_pad = M rounded up to 256;
+ * element (r, c) at (((r/32)*(D/4) + c/4)*32 + r%32)*4 + c%4), together with its raw bf16 copy xb (M, D) row-major and
+ * per-row partial sums stats[m_pad][VITTF_LN_SLOTS] = (sum, sum of squares) over the columns of a slot (unused slots: 0).
+ *   consumer (colsum != NULL; epi 0, 1, 3, 4): A = xb, W = bf16(W*gamma), bias = b + W beta, `stats` describes the rows
+ *            of x (K = D columns); the epilogue applies mean / rstd (eps) per row.
+ *   producer (epi 5, VITTF_EPI_BIAS_RESID_LN): xt += A W^T + bias (read-modify-write of the row-tiled stream by the epilogue
+ *            threads, one row each), out = xb bf16 (M, N) of the updated stream, stats_out slots [0, vittf_gemm_ln_slots(N))
+ *            (one per 128 columns for N % 256 == 0, per 64 otherwise; N must need <= VITTF_LN_SLOTS of them).
+ * vittf_ln_prepare builds xt / xb / stats (slot 0 = full sums, the other slots zero) from a row-major stream. */
+#define VITTF_LN_SLOTS 8
+typedef struct {
+    const float* colsum;
+    const float* stats;      /* (m_pad, VITTF_LN_SLOTS, 2) */
+    float eps;
+    float* xt;
+    float* stats_out;        /* (m_pad, VITTF_LN_SLOTS, 2) */
+    int64_t m_pad;
+} vittf_ln_fold;
+int vittf_gemm_ln_slots(int N);
+int vittf_gemm_bf16_ln(const void* A, const void* W, const float* bias, void* out, void* out2, int M, int N, int K,
+                       int epi, int tokens, int tok_pad, const vittf_ln_fold* ln, void* stream);
+int vittf_ln_prepare(const float* x, float* xt, void* xb_bf16, float* stats, int64_t rows, int64_t m_pad, int D,
+                     void* stream);
 /* softmax(Q K^T / 8) V per (image, head); qk (B*tokens, 2D) bf16, vt as written by epi 3,
  * out bf16 (B*tokens, D). */
 int vittf_attention(const void* qk, const void* vt, void* out, int B, int tokens, int tok_pad, int heads, void* stream);

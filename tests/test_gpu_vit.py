@@ -271,3 +271,23 @@ def test_other_backbones_match_oracle(arch, depth):
     out = infer.feature_volume(vol, model, patch, 8, batch_size=5).cpu()
     assert out.shape == ref.shape and out.dtype == torch.float16
     assert _cos_min(out, ref) >= 0.995
+
+
+@pytest.mark.parametrize("switch", ["VITTF_NO_LNFOLD", "VITTF_GEMM_NO_PAIRS"])
+def test_engine_switches(switch):
+    """The engine's two A/B switches select code the default path does not run: VITTF_NO_LNFOLD = separate LayerNorm kernel +
+    reduce-add residual epilogue (the default folds norm1 / norm2 into the GEMMs around them), VITTF_GEMM_NO_PAIRS =
+    single-CTA GEMM tiles (the default runs N % 256 == 0 as CTA pairs, tcgen05 cta_group::2).  The golden feature volumes, the
+    full-depth ViT-S/8 and ViT-B/8 checks and the GEMM unit tests must hold under both."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    here = Path(__file__).resolve().parent
+    env = dict(os.environ)
+    env[switch] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", str(here / "test_gpu_vit.py"), str(here / "test_gpu_gemm.py"), "-x", "-q", "-m", "gpu",
+                        "-p", "no:cacheprovider", "-k",
+                        "reference_golden or full_depth or other_backbones or (test_gemm and not test_gemm_ln)"],
+                       env=env, capture_output=True, text=True, cwd=str(here.parent))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -25,7 +25,13 @@ class VitConfig(C.Structure):
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b",
-                                          "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+                                          "fc1_w", "fc1_b", "fc2_w", "fc2_b", "qkv_colsum", "fc1_colsum")]
+
+
+class LnFold(C.Structure):
+    """vittf_ln_fold (include/vittf.h): LayerNorm folded into the GEMM epilogues."""
+    _fields_ = [("colsum", C.c_void_p), ("stats", C.c_void_p), ("eps", C.c_float),
+                ("xt", C.c_void_p), ("stats_out", C.c_void_p), ("m_pad", C.c_int64)]
 
 
 class BlsParams(C.Structure):
@@ -35,7 +41,8 @@ class BlsParams(C.Structure):
 
 U8, F16, BF16, F32, F64 = 0, 1, 2, 3, 4
 DTYPE_CODE = {torch.uint8: U8, torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32, torch.float64: F64}
-EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_QKV_SPLIT, EPI_KFEAT_F16 = range(5)
+EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_QKV_SPLIT, EPI_KFEAT_F16, EPI_BIAS_RESID_LN = range(6)
+LN_SLOTS = 8            # VITTF_LN_SLOTS
 SIM_NS, SIM_REFNTF, SIM_LEGACY, SIM_CLAMP_MEAN = 0, 1, 2, 3
 
 _p, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
@@ -60,6 +67,9 @@ _SIGNATURES = {
     "vittf_attention_workspace_bytes": (_i64, [_i, _i, _i]),
     "vittf_attention_prescaled": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i64, _p]),
     "vittf_layernorm": (_i, [_p, _p, _p, _p, _i64, _i, _p]),
+    "vittf_gemm_ln_slots": (_i, [_i]),
+    "vittf_gemm_bf16_ln": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "vittf_ln_prepare": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _p]),
     "vittf_patch_embed": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "vittf_sample_prototypes": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _p]),
     "vittf_sim_lowres_layout": (_i, [_i, _i, _i, _i, _i, _p]),

@@ -108,6 +108,48 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// ---- CTA pairs (thread-block cluster of 2, tcgen05 cta_group::2) ---------------------------------------------
+// In a cluster launch the shared::cta window of CTA rank r sits at r << 24 inside the shared::cluster window, so clearing
+// bit 24 of a local shared-memory address names the SAME offset in the even (leader) CTA of the pair.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {       // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in the leader CTA (release at cluster scope: orders this thread's earlier
+// TMEM reads, fenced with tcgen05.fence::before_thread_sync, before the leader's next MMA into that accumulator)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("vittf: cluster mbarrier timeout block (%d,%d,%d) thread %d bar %u parity %u\n", blockIdx.x, blockIdx.y,
+                   blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
 // Bounded wait: a protocol bug turns into a trap (launch failure) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -141,6 +183,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// CTA-pair load: the tile lands in THIS CTA's shared memory, its bytes are counted on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(m), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
@@ -168,6 +218,10 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                  "r"(smem_u32(src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// asynchronous HBM -> L2 prefetch of a contiguous block (16-byte aligned address, size a multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the smem source of all but the N most recent bulk groups has been read
 template <int N>
@@ -188,6 +242,17 @@ template <int NCOLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(NCOLS) : "memory");
 }
+// CTA pair: one warp of EACH CTA executes these (same shared-memory offset for the result in both)
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(NCOLS) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -195,6 +260,14 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 // arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// CTA pair: the arrive is multicast to the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(static_cast<uint16_t>(3))
                  : "memory");
 }
 
@@ -222,6 +295,19 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// CTA pair (issued by the leader only): D[256 x N] (+)= A[256 x 16] * B[N x 16]^T with A rows and B rows split over the two
+// CTAs' shared memories (same offsets) and D rows over their tensor memories
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");

@@ -12,6 +12,20 @@
 //                              happens in L2, the SM never reads the fp32 residual stream).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1 -- essential here because K is short (384..3072).
+//
+// LayerNorm without a LayerNorm pass (the pre-LN blocks compute LN(x) W^T + b twice per block).  With gamma folded into
+// the weight (W' = W * gamma, host side) and mean / rstd of the row known,
+//     LN(x) W^T + b  =  rstd * (x W'^T  -  mean * colsum(W'))  +  (b + W beta),
+// so the CONSUMER GEMMs (qkv, fc1, K features) take the raw bf16 copy of the residual stream as their A operand and
+// apply the two row scalars in the epilogue (2 FMAs per element instead of 1 add).  The PRODUCER GEMMs (proj, fc2:
+// VITTF_EPI_BIAS_RESID_LN) own the residual stream: their epilogue reads x, adds the accumulator, writes x back, writes
+// the bf16 copy (TMA store) and the per-row partial sums (sum, sum of squares) of its 128-column slice -- the consumer adds
+// the 2 N / BN partials of a row.  An epilogue thread owns one accumulator ROW, so the fp32 stream is kept in a row-tiled
+// layout xt[M/32][D/4][32 rows][4 columns]: a warp's 16-byte accesses are 512 contiguous bytes, nothing is staged through
+// shared memory, and the row sums need no shuffles.  Against the reduce-add epilogue + layernorm_kernel this removes one
+// read of x (fp32) per LayerNorm and the launch itself.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -23,12 +37,18 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int STAGING_BYTES = 32 * 128;  // one 32-row x 128-byte tile per epilogue warp
 
-template <int BN>
+// CG = 2: CTA pair (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256 x BN tile: each CTA stages ITS 128 rows of
+// A and ITS half of the W rows (BN / 2), the leader's MMA reads both halves, each CTA's tensor memory receives its 128
+// accumulator rows.  Per CTA and K block that is 32 KB from L2 instead of 48 KB for the same 128 x 256 x 64 MACs -- the
+// single-CTA kernel at 1.28 PFLOP/s pulls ~52 B/clk/SM, which is what the L2 slices deliver chip-wide (the GEMMs were
+// L2-bandwidth-bound, not tensor-bound).
+template <int BN, int CG = 1>
 struct GemmCfg {
-    static constexpr int STAGES = BN <= 128 ? 6 : 4;
+    static constexpr int B_ROWS = BN / CG;                     // W rows staged per CTA
+    static constexpr int STAGES = B_ROWS <= 128 ? 6 : 4;
     static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;   // TMEM column offset of the second accumulator
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 1024 + 512;
@@ -40,6 +60,13 @@ struct GemmParams {
     void* out2;
     int M, N, K;
     int tokens, tok_pad, heads;
+    // LayerNorm folded into the linear layers around it (see the header comment):
+    const float* colsum;      // consumer: (N) sum_k W'[n][k]; nullptr = plain bias epilogue
+    const float2* stats;      // consumer: (m_pad, VITTF_LN_SLOTS) partial (sum, sum of squares) of every row of the fp32 source of A
+    float inv_k, eps;
+    float* xt;                // producer (VITTF_EPI_BIAS_RESID_LN): row-tiled fp32 residual stream, read-modify-write
+    float2* stats_out;        // producer: (m_pad, VITTF_LN_SLOTS), slots [0, 2 N / BN) written
+    int64_t m_pad;            // M rounded up to a multiple of 128
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), erf from Abramowitz-Stegun 7.1.28
@@ -97,11 +124,12 @@ __device__ __forceinline__ void gelu_tanh2(float& x0, float& x1) {
 // byte offset of 16-byte chunk `chunk` of row `row` inside a 128B-swizzled 32 x 128 B staging tile
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_out, GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
+    static_assert(CG == 1 || CG == 2, "single CTA or CTA pair");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -114,7 +142,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform role index
     const int lane = threadIdx.x & 31;
-    const int m_tiles = (p.M + BM - 1) / BM;
+    // a tile = BM * CG rows x BN columns, owned by one CTA or one CTA pair; `unit` walks the tiles of this CTA (pair)
+    const int rank = CG == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+    const int unit0 = blockIdx.x / CG, unit_stride = gridDim.x / CG;
+    const int m_tiles = (p.M + BM * CG - 1) / (BM * CG);
     const int n_tiles = p.N / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = p.K / BK;
@@ -126,13 +157,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full[i], 1);
-            ptx::mbar_init(&tmem_empty[i], EPI_THREADS);
+            ptx::mbar_init(&tmem_empty[i], CG * EPI_THREADS);     // the leader's barrier collects both CTAs' epilogue threads
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 2) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (warp == 2) {
+        if constexpr (CG == 2) ptx::tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+        else ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync_all();      // the peer's barriers are initialised before anything is signalled on them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -145,26 +180,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         ptx::prefetch_tmap(&tm_b);
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
             const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
             for (int kb = 0; kb < num_kb; ++kb) {
                 ptx::mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                ptx::tma_load_2d(sa, &tm_a, &full[stage], kb * BK, m_blk * BM);
-                ptx::tma_load_2d(sa + Cfg::A_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN);
+                if constexpr (CG == 2) {
+                    // both CTAs' bytes are counted on the leader's barrier (the only one its MMA issuer waits on)
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                    ptx::tma_load_2d_pair(sa, &tm_a, &full[stage], kb * BK, (m_blk * 2 + rank) * BM);
+                    ptx::tma_load_2d_pair(sa + Cfg::A_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN + rank * Cfg::B_ROWS);
+                } else {
+                    ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    ptx::tma_load_2d(sa, &tm_a, &full[stage], kb * BK, m_blk * BM);
+                    ptx::tma_load_2d(sa + Cfg::A_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN);
+                }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && ptx::elect_one()) {
+    } else if (warp == 1 && rank == 0 && ptx::elect_one()) {
         // ---------------- MMA issuer ----------------
-        constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, BN);
+        constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM * CG, BN);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
             const int as = it & 1;
-            ptx::mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+            if constexpr (CG == 2) ptx::mbar_wait_cluster(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+            else ptx::mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -173,11 +216,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 const uint64_t adesc = ptx::smem_desc_k_sw128(sa);
                 const uint64_t bdesc = ptx::smem_desc_k_sw128(sa + Cfg::A_BYTES);
+                if constexpr (CG == 2) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 step inside the swizzle row
-                    ptx::umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                ptx::tc_commit(&empty[stage]);
-                if (kb == num_kb - 1) ptx::tc_commit(&tmem_full[as]);
+                    for (int k = 0; k < BK / 16; ++k) ptx::umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    ptx::tc_commit_pair(&empty[stage]);          // frees the stage in both CTAs
+                    if (kb == num_kb - 1) ptx::tc_commit_pair(&tmem_full[as]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 step inside the swizzle row
+                        ptx::umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    ptx::tc_commit(&empty[stage]);
+                    if (kb == num_kb - 1) ptx::tc_commit(&tmem_full[as]);
+                }
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -189,12 +239,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         constexpr int CHUNKS = BN / 2 / 32;
         if (ptx::elect_one()) ptx::prefetch_tmap(&tm_out);
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        // accumulator drained: tell the (leader's) MMA issuer
+        auto release_acc = [&](int as) {
+            ptx::tc_fence_before();
+            if constexpr (CG == 2) ptx::mbar_arrive_leader(&tmem_empty[as]);
+            else ptx::mbar_arrive(&tmem_empty[as]);
+        };
+        for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++it) {
+            const int n_blk = tile % n_tiles;
+            const int m_blk = (tile / n_tiles) * CG + rank;      // this CTA's 128-row block
             const int as = it & 1;
             const int row0 = m_blk * BM + q * 32;
             const int row = row0 + lane;
             const int n0 = n_blk * BN + half * (BN / 2);
+            // LayerNorm fold, consumer side: the two row scalars (plain epilogue: rstd = 1, -mean * rstd = 0)
+            float rstd = 1.0f, nmr = 0.0f;
+            const float* cs = p.bias;
+            if (p.colsum != nullptr) {
+                // the row's partial sums: 64 contiguous bytes, four independent 16-byte loads (unused slots hold zeros)
+                static_assert(VITTF_LN_SLOTS == 8, "four float4 loads per row");
+                const float4* st = reinterpret_cast<const float4*>(p.stats) + static_cast<size_t>(row) * 4;
+                const float4 t0 = __ldg(st), t1 = __ldg(st + 1), t2 = __ldg(st + 2), t3 = __ldg(st + 3);
+                const float sum = ((t0.x + t0.z) + (t1.x + t1.z)) + ((t2.x + t2.z) + (t3.x + t3.z));
+                const float sq = ((t0.y + t0.w) + (t1.y + t1.w)) + ((t2.y + t2.w) + (t3.y + t3.w));
+                const float mean = sum * p.inv_k;
+                rstd = rsqrtf(fmaxf(sq * p.inv_k - mean * mean, 0.0f) + p.eps);
+                nmr = -mean * rstd;
+                cs = p.colsum;
+            }
+            // producer side: this thread's row of the tile in the row-tiled stream; the first 32 columns are requested
+            // before the accumulator is waited for
+            float4* xrow = nullptr;
+            float4 xo[8];
+            if constexpr (EPI == VITTF_EPI_BIAS_RESID_LN) {
+                // a warp's slice of the tile (32 rows x BN/2 columns) is ONE contiguous block of the row-tiled stream
+                auto slice = [&](int mb, int nb) {
+                    return reinterpret_cast<float4*>(p.xt) + (static_cast<size_t>(mb * 4 + q) * (p.N / 4) + (nb * BN + half * (BN / 2)) / 4) * 32;
+                };
+                xrow = slice(m_blk, n_blk) + lane;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xo[i] = __ldcs(xrow + i * 32);
+            }
             ptx::mbar_wait(&tmem_full[as], (it >> 1) & 1);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE + half * (BN / 2);
@@ -220,10 +305,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                    v[i + 0] = __uint_as_float(acc[i + 0]) + b.x;
-                    v[i + 1] = __uint_as_float(acc[i + 1]) + b.y;
-                    v[i + 2] = __uint_as_float(acc[i + 2]) + b.z;
-                    v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + n + i));
+                    v[i + 0] = fmaf(__uint_as_float(acc[i + 0]), rstd, fmaf(nmr, s4.x, b.x));
+                    v[i + 1] = fmaf(__uint_as_float(acc[i + 1]), rstd, fmaf(nmr, s4.y, b.y));
+                    v[i + 2] = fmaf(__uint_as_float(acc[i + 2]), rstd, fmaf(nmr, s4.z, b.z));
+                    v[i + 3] = fmaf(__uint_as_float(acc[i + 3]), rstd, fmaf(nmr, s4.w, b.w));
                 }
             };
             auto put_bf16 = [&](int chunk0, const float (&v)[32]) {   // 32 values -> 4 chunks of 8 bf16
@@ -240,8 +326,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     float v[32];
                     load_biased(c, v);
                     if (c == CHUNKS - 1) {       // accumulator fully read: give it back to the MMA warp
-                        ptx::tc_fence_before();
-                        ptx::mbar_arrive(&tmem_empty[as]);
+                        release_acc(as);
                     }
                     staging_free();
 #pragma unroll
@@ -249,6 +334,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         *reinterpret_cast<float4*>(stg + swz(lane, i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     stage_out(n0 + c * 32, true);
                 }
+            } else if constexpr (EPI == VITTF_EPI_BIAS_RESID_LN) {
+                static_assert(CHUNKS % 2 == 0, "the bf16 copy is staged in 64-column tiles");
+                float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
+                    float v[32];
+                    load_biased(c, v);
+                    if (c == CHUNKS - 1) {
+                        release_acc(as);
+                    }
+                    float4 xn[8];
+                    if (c + 1 < CHUNKS) {        // next 32 columns of x: in flight while this chunk is finished
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xn[i] = __ldcs(xrow + ((c + 1) * 8 + i) * 32);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[4 * i + 0] += xo[i].x;
+                        v[4 * i + 1] += xo[i].y;
+                        v[4 * i + 2] += xo[i].z;
+                        v[4 * i + 3] += xo[i].w;
+                        xrow[(c * 8 + i) * 32] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        sum += (v[4 * i] + v[4 * i + 1]) + (v[4 * i + 2] + v[4 * i + 3]);
+                        sq = fmaf(v[4 * i], v[4 * i], sq);
+                        sq = fmaf(v[4 * i + 1], v[4 * i + 1], sq);
+                        sq = fmaf(v[4 * i + 2], v[4 * i + 2], sq);
+                        sq = fmaf(v[4 * i + 3], v[4 * i + 3], sq);
+                    }
+                    if ((c & 1) == 0) staging_free();
+                    put_bf16((c & 1) * 4, v);
+                    if (c & 1) stage_out(n0 + (c - 1) * 32, false);
+                    if (c + 1 < CHUNKS) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xo[i] = xn[i];
+                    }
+                }
+                p.stats_out[static_cast<size_t>(row) * VITTF_LN_SLOTS + n_blk * 2 + half] = make_float2(sum, sq);
             } else if constexpr (EPI == VITTF_EPI_BIAS_BF16 || EPI == VITTF_EPI_BIAS_GELU_BF16 || EPI == VITTF_EPI_QKV_SPLIT) {
                 static_assert(CHUNKS % 2 == 0, "bf16 epilogues stage 64-column tiles");
                 const int two_d = (p.N / 3) * 2;
@@ -258,8 +380,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     load_biased(c, v0);
                     load_biased(c + 1, v1);
                     if (c == CHUNKS - 2) {
-                        ptx::tc_fence_before();
-                        ptx::mbar_arrive(&tmem_empty[as]);
+                        release_acc(as);
                     }
                     const int n = n0 + c * 32;
                     if (EPI == VITTF_EPI_QKV_SPLIT && n >= two_d) {
@@ -304,8 +425,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                     float v[32];
                     load_biased(c, v);
                     if (c == CHUNKS - 1) {
-                        ptx::tc_fence_before();
-                        ptx::mbar_arrive(&tmem_empty[as]);
+                        release_acc(as);
                     }
                     if (live) {
                         uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + orow * p.N + n0 + c * 32);
@@ -325,13 +445,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         if (ptx::elect_one()) ptx::bulk_wait_all();   // staging tiles must outlive their TMA reads; writes complete
     }
     ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) {
+        ptx::cluster_sync_all();      // neither CTA leaves (or frees tensor memory) while the pair's MMAs / remote arrives are in flight
+        if (warp == 2) ptx::tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    } else {
+        __syncthreads();
+        if (warp == 2) ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG = 1>
 int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     CUtensorMap tm_a, tm_b, tm_out;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
@@ -342,7 +467,7 @@ int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t 
     {
         uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
         uint64_t strides[1] = {static_cast<uint64_t>(p.K) * 2};
-        uint32_t box[2] = {BK, BN};
+        uint32_t box[2] = {BK, static_cast<uint32_t>(Cfg::B_ROWS)};
         VITTF_CHECK(vittf_make_tmap(&tm_b, W, 2, 2, dims, strides, box, true));
     }
     if (EPI == VITTF_EPI_BIAS_RESID_F32) {            // fp32 (M, N), 32 x 32 tiles, reduce-add
@@ -359,20 +484,78 @@ int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t 
         uint32_t box[2] = {64, 32};
         VITTF_CHECK(vittf_make_tmap(&tm_out, p.out, 2, 2, dims, strides, box, true));
     }
-    auto kern = gemm_bf16_kernel<BN, EPI>;
+    auto kern = gemm_bf16_kernel<BN, EPI, CG>;
     static PerDeviceMemo configured;
     if (!configured.cur()) {
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured.cur() = 1;
     }
-    const int tiles = ceil_div(p.M, BM) * (p.N / BN);
-    const int grid = tiles < vittf_num_sms() ? tiles : vittf_num_sms();
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, tm_out, p);
+    const int tiles = ceil_div(p.M, BM * CG) * (p.N / BN);          // tiles of a CTA (CG = 1) or of a CTA pair
+    const int units = vittf_num_sms() / CG;
+    const int grid = (tiles < units ? tiles : units) * CG;
+    if (CG == 1) {
+        kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, tm_out, p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;          // CTA pairs: the two CTAs of a cluster share a TPC
+        attr[0].val.clusterDim.x = CG;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        VITTF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, tm_out, p));
+    }
     VITTF_CHECK_CUDA(cudaGetLastError());
     vittf_count_launches(1);
     return VITTF_OK;
 }
 
+}  // namespace
+
+namespace {
+int gemm_dispatch(const void* A, const void* W, GemmParams p, int epi, cudaStream_t s) {
+    const int N = p.N;
+    static const bool pairs = getenv("VITTF_GEMM_NO_PAIRS") == nullptr;       // A/B switch: single-CTA tiles only
+    // widest tile that divides N (a wider tile halves the shared-memory operand traffic per MMA); the bf16
+    // epilogues stage 64-column tiles per warp, so they use 256 or 128; the fp32 reduce-add also takes 192
+#define VITTF_GEMM_BF16OUT(E)                                                       \
+    do {                                                                            \
+        if (N % 256 == 0 && pairs) return launch_gemm<256, E, 2>(A, W, p, s);      \
+        if (N % 256 == 0) return launch_gemm<256, E>(A, W, p, s);                   \
+        return launch_gemm<128, E>(A, W, p, s);                                     \
+    } while (0)
+    switch (epi) {
+        case VITTF_EPI_BIAS_BF16: VITTF_GEMM_BF16OUT(VITTF_EPI_BIAS_BF16);
+        case VITTF_EPI_BIAS_GELU_BF16: VITTF_GEMM_BF16OUT(VITTF_EPI_BIAS_GELU_BF16);
+        case VITTF_EPI_BIAS_RESID_F32:
+            if (N % 256 == 0 && pairs) return launch_gemm<256, VITTF_EPI_BIAS_RESID_F32, 2>(A, W, p, s);
+            if (N % 256 == 0) return launch_gemm<256, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
+            if (N % 192 == 0) return launch_gemm<192, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
+            return launch_gemm<128, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
+        case VITTF_EPI_BIAS_RESID_LN:
+            VITTF_REQUIRE(p.xt && p.stats_out, "vittf_gemm_bf16_ln: the residual-stream epilogue needs xt and stats_out");
+            VITTF_REQUIRE(vittf_gemm_ln_slots(N) <= VITTF_LN_SLOTS, "vittf_gemm_bf16_ln: N=%d needs %d partial-sum slots (max %d)", N,
+                          vittf_gemm_ln_slots(N), VITTF_LN_SLOTS);
+            VITTF_GEMM_BF16OUT(VITTF_EPI_BIAS_RESID_LN);
+        case VITTF_EPI_QKV_SPLIT:
+            VITTF_REQUIRE(p.out2 && N % 3 == 0 && (N / 3) % 64 == 0 && p.tokens > 0 && p.tok_pad >= p.tokens && p.M % p.tokens == 0,
+                          "vittf_gemm_bf16: bad QKV split arguments (N=%d tokens=%d tok_pad=%d M=%d)", N, p.tokens,
+                          p.tok_pad, p.M);
+            p.heads = N / 3 / 64;
+            VITTF_GEMM_BF16OUT(VITTF_EPI_QKV_SPLIT);
+        case VITTF_EPI_KFEAT_F16:
+            VITTF_REQUIRE(p.tokens > 1 && p.M % p.tokens == 0, "vittf_gemm_bf16: bad K-feature arguments");
+            return launch_gemm<128, VITTF_EPI_KFEAT_F16>(A, W, p, s);
+        default: VITTF_REQUIRE(false, "vittf_gemm_bf16: unknown epilogue %d", epi);
+    }
+#undef VITTF_GEMM_BF16OUT
+    return VITTF_OK;
+}
 }  // namespace
 
 extern "C" int vittf_gemm_bf16(const void* A, const void* W, const float* bias, void* out, void* out2, int M, int N,
@@ -381,33 +564,34 @@ extern "C" int vittf_gemm_bf16(const void* A, const void* W, const float* bias, 
     VITTF_REQUIRE(M > 0 && N > 0 && K > 0, "vittf_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
     VITTF_REQUIRE(K % BK == 0, "vittf_gemm_bf16: K=%d must be a multiple of %d", K, BK);
     VITTF_REQUIRE(N % 128 == 0, "vittf_gemm_bf16: N=%d must be a multiple of 128", N);
-    GemmParams p{bias, out, out2, M, N, K, tokens, tok_pad, 0};
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // widest tile that divides N (a wider tile halves the shared-memory operand traffic per MMA); the bf16
-    // epilogues stage 64-column tiles per warp, so they use 256 or 128; the fp32 reduce-add also takes 192
-#define VITTF_GEMM_BF16OUT(E)                                             \
-    do {                                                                  \
-        if (N % 256 == 0) return launch_gemm<256, E>(A, W, p, s);         \
-        return launch_gemm<128, E>(A, W, p, s);                           \
-    } while (0)
-    switch (epi) {
-        case VITTF_EPI_BIAS_BF16: VITTF_GEMM_BF16OUT(VITTF_EPI_BIAS_BF16);
-        case VITTF_EPI_BIAS_GELU_BF16: VITTF_GEMM_BF16OUT(VITTF_EPI_BIAS_GELU_BF16);
-        case VITTF_EPI_BIAS_RESID_F32:
-            if (N % 256 == 0) return launch_gemm<256, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
-            if (N % 192 == 0) return launch_gemm<192, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
-            return launch_gemm<128, VITTF_EPI_BIAS_RESID_F32>(A, W, p, s);
-        case VITTF_EPI_QKV_SPLIT:
-            VITTF_REQUIRE(out2 && N % 3 == 0 && (N / 3) % 64 == 0 && tokens > 0 && tok_pad >= tokens && M % tokens == 0,
-                          "vittf_gemm_bf16: bad QKV split arguments (N=%d tokens=%d tok_pad=%d M=%d)", N, tokens,
-                          tok_pad, M);
-            p.heads = N / 3 / 64;
-            VITTF_GEMM_BF16OUT(VITTF_EPI_QKV_SPLIT);
-        case VITTF_EPI_KFEAT_F16:
-            VITTF_REQUIRE(tokens > 1 && M % tokens == 0, "vittf_gemm_bf16: bad K-feature arguments");
-            return launch_gemm<128, VITTF_EPI_KFEAT_F16>(A, W, p, s);
-        default: VITTF_REQUIRE(false, "vittf_gemm_bf16: unknown epilogue %d", epi);
+    VITTF_REQUIRE(epi != VITTF_EPI_BIAS_RESID_LN, "vittf_gemm_bf16: epilogue %d needs vittf_gemm_bf16_ln", epi);
+    GemmParams p{};
+    p.bias = bias; p.out = out; p.out2 = out2; p.M = M; p.N = N; p.K = K; p.tokens = tokens; p.tok_pad = tok_pad;
+    return gemm_dispatch(A, W, p, epi, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vittf_gemm_ln_slots(int N) { return N <= 0 ? -1 : 2 * N / (N % 256 == 0 ? 256 : 128); }
+
+extern "C" int vittf_gemm_bf16_ln(const void* A, const void* W, const float* bias, void* out, void* out2, int M, int N,
+                                  int K, int epi, int tokens, int tok_pad, const vittf_ln_fold* ln, void* stream) {
+    VITTF_REQUIRE(A && W && bias && out && ln, "vittf_gemm_bf16_ln: null pointer");
+    VITTF_REQUIRE(M > 0 && N > 0 && K > 0, "vittf_gemm_bf16_ln: empty problem M=%d N=%d K=%d", M, N, K);
+    VITTF_REQUIRE(K % BK == 0, "vittf_gemm_bf16_ln: K=%d must be a multiple of %d", K, BK);
+    VITTF_REQUIRE(N % 128 == 0, "vittf_gemm_bf16_ln: N=%d must be a multiple of 128", N);
+    VITTF_REQUIRE(ln->m_pad >= M && ln->m_pad % 256 == 0, "vittf_gemm_bf16_ln: m_pad=%lld must be M rounded up to a multiple of 256",
+                  (long long)ln->m_pad);
+    GemmParams p{};
+    p.bias = bias; p.out = out; p.out2 = out2; p.M = M; p.N = N; p.K = K; p.tokens = tokens; p.tok_pad = tok_pad;
+    p.m_pad = ln->m_pad;
+    if (ln->colsum) {                 // consumer: A is the raw bf16 copy of the stream, W the gamma-folded weight
+        VITTF_REQUIRE(ln->stats, "vittf_gemm_bf16_ln: colsum given without row statistics");
+        VITTF_REQUIRE(epi != VITTF_EPI_BIAS_RESID_F32, "vittf_gemm_bf16_ln: the reduce-add epilogue takes no LayerNorm fold");
+        p.colsum = ln->colsum;
+        p.stats = reinterpret_cast<const float2*>(ln->stats);
+        p.inv_k = 1.0f / static_cast<float>(K);
+        p.eps = ln->eps;
     }
-#undef VITTF_GEMM_BF16OUT
-    return VITTF_OK;
+    p.xt = ln->xt;
+    p.stats_out = reinterpret_cast<float2*>(ln->stats_out);
+    return gemm_dispatch(A, W, p, epi, static_cast<cudaStream_t>(stream));
 }

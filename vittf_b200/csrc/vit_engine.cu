@@ -32,6 +32,8 @@ struct Workspace {
     __nv_bfloat16* vt;    // (B*heads*64, tok_pad)
     __nv_bfloat16* att;   // attention output (M, D)
     __nv_bfloat16* hid;   // MLP hidden (M, 4D)
+    float* stats;         // LayerNorm fold: (m_pad, VITTF_LN_SLOTS) partial (sum, sum of squares) of the rows of x
+    int64_t m_pad;
     void* attn_ws;        // per-CTA flags of the two-pass attention
     int64_t attn_ws_bytes;
     int64_t vt_bytes;
@@ -44,8 +46,10 @@ Workspace carve(const vittf_vit_config& c, int batch, int tokens, uint8_t* base)
     const int D = c.embed_dim;
     int64_t off = 0;
     auto take = [&](int64_t bytes) { uint8_t* p = base ? base + off : nullptr; off += align256(bytes); return p; };
-    w.x = reinterpret_cast<float*>(take(M * D * 4));
+    w.m_pad = (M + 255) / 256 * 256;          // the row-tiled stream of the LayerNorm-folded path holds whole 256-row pair tiles
+    w.x = reinterpret_cast<float*>(take(w.m_pad * D * 4));
     w.xn = reinterpret_cast<__nv_bfloat16*>(take(M * D * 2));
+    w.stats = reinterpret_cast<float*>(take(w.m_pad * VITTF_LN_SLOTS * 8));
     w.qk = reinterpret_cast<__nv_bfloat16*>(take(M * 2 * D * 2));
     w.vt_bytes = static_cast<int64_t>(batch) * D * tok_pad_of(tokens) * 2;
     w.vt = reinterpret_cast<__nv_bfloat16*>(take(w.vt_bytes));
@@ -114,6 +118,20 @@ extern "C" int vittf_vit_create(vittf_vit** out, const vittf_vit_config* cfg, co
     v->blocks = new (std::nothrow) vittf_block_weights[cfg->depth];
     if (!v->blocks) { delete v; VITTF_REQUIRE(false, "vittf_vit_create: out of host memory"); }
     for (int i = 0; i < cfg->depth; ++i) v->blocks[i] = blocks_host[i];
+    for (int i = 0; i < cfg->depth; ++i) {
+        const bool fold = blocks_host[i].qkv_colsum != nullptr;
+        if (fold != (blocks_host[0].qkv_colsum != nullptr) || fold != (blocks_host[i].fc1_colsum != nullptr)) {
+            delete[] v->blocks;
+            delete v;
+            VITTF_REQUIRE(false, "vittf_vit_create: qkv_colsum / fc1_colsum must be set for every block or for none (block %d)", i);
+        }
+    }
+    if (blocks_host[0].qkv_colsum != nullptr && (cfg->mlp_hidden < 2 * cfg->embed_dim || vittf_gemm_ln_slots(cfg->embed_dim) > VITTF_LN_SLOTS)) {
+        delete[] v->blocks;
+        delete v;
+        VITTF_REQUIRE(false, "vittf_vit_create: the LayerNorm-folded path needs mlp_hidden >= 2 D (token staging) and D = %d within %d "
+                      "partial-sum slots", cfg->embed_dim, VITTF_LN_SLOTS);
+    }
     v->patch_w = patch_w;
     v->patch_b = patch_b;
     v->max_batch = max_batch;
@@ -157,6 +175,40 @@ extern "C" int vittf_vit_k_features(vittf_vit* v, const void* vol, int vol_dtype
     const int tok_pad = tok_pad_of(tokens);
     // padding columns of V^T are read (times P = 0) by the last key block: they must be finite
     VITTF_CHECK_CUDA(cudaMemsetAsync(w.vt, 0, w.vt_bytes, s));
+    const bool fold = v->blocks[0].qkv_colsum != nullptr;
+    if (fold) {
+        // LayerNorm folded into the GEMMs (gemm.cu): x = row-tiled fp32 stream, xn = its raw bf16 copy, stats = row sums.
+        // The patch embedding writes row-major tokens into the (still unused) MLP hidden buffer; one pass re-tiles them.
+        float* x_rm = reinterpret_cast<float*>(w.hid);
+        VITTF_CHECK(vittf_patch_embed(vol, vol_dtype, X, Y, Z, axis, s0, s1, im0, im1, c.patch, D, minmax2, v->patch_w,
+                                      v->patch_b, pos_embed, x_rm, stream));
+        VITTF_CHECK(vittf_ln_prepare(x_rm, w.x, w.xn, w.stats, M, w.m_pad, D, stream));
+        vittf_ln_fold consume{};
+        consume.stats = w.stats; consume.eps = 1e-6f; consume.m_pad = w.m_pad;
+        vittf_ln_fold produce{};
+        produce.xt = w.x; produce.stats_out = w.stats; produce.m_pad = w.m_pad;
+        for (int l = 0; l + 1 < c.depth; ++l) {
+            const vittf_block_weights& bw = v->blocks[l];
+            consume.colsum = bw.qkv_colsum;
+            { ScopedTimer t(v, 1, s);
+              VITTF_CHECK(vittf_gemm_bf16_ln(w.xn, bw.qkv_w, bw.qkv_b, w.qk, w.vt, M, 3 * D, D, VITTF_EPI_QKV_SPLIT, tokens, tok_pad, &consume, stream)); }
+            { ScopedTimer t(v, 0, s);
+              VITTF_CHECK(vittf_attention_prescaled(w.qk, w.vt, w.att, B, tokens, tok_pad, c.num_heads, w.attn_ws, w.attn_ws_bytes, stream)); }
+            { ScopedTimer t(v, 1, s);
+              VITTF_CHECK(vittf_gemm_bf16_ln(w.att, bw.proj_w, bw.proj_b, w.xn, nullptr, M, D, D, VITTF_EPI_BIAS_RESID_LN, tokens, tok_pad, &produce, stream)); }
+            consume.colsum = bw.fc1_colsum;
+            { ScopedTimer t(v, 1, s);
+              VITTF_CHECK(vittf_gemm_bf16_ln(w.xn, bw.fc1_w, bw.fc1_b, w.hid, nullptr, M, c.mlp_hidden, D, VITTF_EPI_BIAS_GELU_BF16, tokens, tok_pad, &consume, stream)); }
+            { ScopedTimer t(v, 1, s);
+              VITTF_CHECK(vittf_gemm_bf16_ln(w.hid, bw.fc2_w, bw.fc2_b, w.xn, nullptr, M, D, c.mlp_hidden, VITTF_EPI_BIAS_RESID_LN, tokens, tok_pad, &produce, stream)); }
+        }
+        // last block: norm1 + K rows [D, 2D) of attn.qkv only
+        const vittf_block_weights& last = v->blocks[c.depth - 1];
+        consume.colsum = last.qkv_colsum + D;
+        const __nv_bfloat16* wk = static_cast<const __nv_bfloat16*>(last.qkv_w) + static_cast<size_t>(D) * D;
+        VITTF_CHECK(vittf_gemm_bf16_ln(w.xn, wk, last.qkv_b + D, out_k_f16, nullptr, M, D, D, VITTF_EPI_KFEAT_F16, tokens, tok_pad, &consume, stream));
+        return VITTF_OK;
+    }
     VITTF_CHECK(vittf_patch_embed(vol, vol_dtype, X, Y, Z, axis, s0, s1, im0, im1, c.patch, D, minmax2, v->patch_w,
                                   v->patch_b, pos_embed, w.x, stream));
     for (int l = 0; l + 1 < c.depth; ++l) {

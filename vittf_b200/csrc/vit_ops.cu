@@ -439,6 +439,39 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Entry into the LayerNorm-folded GEMM chain (gemm.cu): the row-major fp32 tokens of the patch embedding become the
+// row-tiled residual stream xt[m_pad/32][D/4][32][4], its raw bf16 copy and the per-row (sum, sum of squares).  One warp
+// per row; runs once per forward (the blocks' LayerNorms themselves never run as a pass).
+// ---------------------------------------------------------------------------------------------
+template <int V4>
+__global__ void __launch_bounds__(256) ln_prepare_kernel(const float* __restrict__ x, float* __restrict__ xt,
+                                                         __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats,
+                                                         int64_t rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    constexpr int D = 128 * V4;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4* xtr = reinterpret_cast<float4*>(xt) + (row >> 5) * (D / 4) * 32 + (row & 31);
+    uint2* yr = reinterpret_cast<uint2*>(xb + row * D);
+    float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float4 v = xr[lane + 32 * i];
+        sum += (v.x + v.y) + (v.z + v.w);
+        sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        xtr[static_cast<int64_t>(lane + 32 * i) * 32] = v;
+        yr[lane + 32 * i] = make_uint2(ptx::pack_bf16x2(v.x, v.y), ptx::pack_bf16x2(v.z, v.w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane < VITTF_LN_SLOTS) stats[row * VITTF_LN_SLOTS + lane] = lane == 0 ? make_float2(sum, sq) : make_float2(0.0f, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
 // AdaptiveAvgPool3d along the slice axis + permute to (D, fX, fY, fZ) + optional fp16 running sum.
 // k: (S, T = f0*f1, D) fp16, D fastest.  One CTA transposes a 32(token) x 64(d) tile through smem.
 // ---------------------------------------------------------------------------------------------
@@ -800,6 +833,30 @@ extern "C" int vittf_layernorm(const float* x, const float* w, const float* b, v
         case 6: layernorm_kernel<6><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
         case 7: layernorm_kernel<7><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
         default: layernorm_kernel<8><<<grid, 256, 0, s>>>(x, w, b, y, rows); break;
+    }
+    VITTF_CHECK_CUDA(cudaGetLastError());
+    vittf_count_launches(1);
+    return VITTF_OK;
+}
+
+extern "C" int vittf_ln_prepare(const float* x, float* xt, void* xb_bf16, float* stats, int64_t rows, int64_t m_pad, int D,
+                                void* stream) {
+    VITTF_REQUIRE(x && xt && xb_bf16 && stats && rows > 0, "vittf_ln_prepare: bad arguments");
+    VITTF_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, "vittf_ln_prepare: D=%d must be a multiple of 128 in [128,1024]", D);
+    VITTF_REQUIRE(m_pad >= rows && m_pad % 256 == 0, "vittf_ln_prepare: m_pad must be rows rounded up to a multiple of 256");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, 8));
+    __nv_bfloat16* y = static_cast<__nv_bfloat16*>(xb_bf16);
+    float2* st = reinterpret_cast<float2*>(stats);
+    switch (D / 128) {
+        case 1: ln_prepare_kernel<1><<<grid, 256, 0, s>>>(x, xt, y, st, rows); break;
+        case 2: ln_prepare_kernel<2><<<grid, 256, 0, s>>>(x, xt, y, st, rows); break;
+        case 3: ln_prepare_kernel<3><<<grid, 256, 0, s>>>(x, xt, y, st, rows); break;
+        case 4: ln_prepare_kernel<4><<<grid, 256, 0, s>>>(x, xt, y, st, rows); break;
+        case 5: ln_prepare_kernel<5><<<grid, 256, 0, s>>>(x, xt, y, st, rows); break;
+        case 6: ln_prepare_kernel<6><<<grid, 256, 0, s>>>(x, xt, y, st, rows); break;
+        case 7: ln_prepare_kernel<7><<<grid, 256, 0, s>>>(x, xt, y, st, rows); break;
+        default: ln_prepare_kernel<8><<<grid, 256, 0, s>>>(x, xt, y, st, rows); break;
     }
     VITTF_CHECK_CUDA(cudaGetLastError());
     vittf_count_launches(1);

@@ -72,6 +72,72 @@ def gemm_bf16(a, w, bias, epi, out=None, out2=None, tokens=0, tok_pad=0):
     return (out, out2) if epi == _lib.EPI_QKV_SPLIT else out
 
 
+def ln_slots(n):
+    """Partial-sum slots the residual-stream epilogue (EPI_BIAS_RESID_LN) writes per row for an N-column stream."""
+    return int(load().vittf_gemm_ln_slots(int(n)))
+
+
+def m_pad_of(rows):
+    return (rows + 255) // 256 * 256
+
+
+def xt_to_rows(xt, rows, D):
+    """Row-tiled stream xt[m_pad/32][D/4][32][4] -> row-major (rows, D) (test / debugging helper, torch glue)."""
+    return xt.view(-1, D // 4, 32, 4).permute(0, 2, 1, 3).reshape(-1, D)[:rows]
+
+
+@_on_device
+def ln_prepare(x):
+    """Row-major fp32 stream (rows, D) -> (xt row-tiled fp32, xb raw bf16 copy, stats (m_pad, LN_SLOTS, 2))."""
+    require_cuda(x)
+    rows, D = x.shape
+    mp = m_pad_of(rows)
+    xt = torch.zeros(mp * D, dtype=torch.float32, device=x.device)
+    xb = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
+    stats = torch.zeros(mp, _lib.LN_SLOTS, 2, dtype=torch.float32, device=x.device)
+    check(load().vittf_ln_prepare(ptr(x), ptr(xt), ptr(xb), ptr(stats), rows, mp, D, stream_ptr(x.device)), "vittf_ln_prepare")
+    return xt, xb, stats
+
+
+@_on_device
+def gemm_bf16_ln(a, w, bias, epi, colsum=None, stats=None, xt=None, out=None, out2=None, tokens=0, tok_pad=0, eps=1e-6,
+                 stats_out=None):
+    """vittf_gemm_bf16_ln: consumer (colsum + stats: LayerNorm of the A operand's fp32 source applied in the epilogue) and /
+    or producer (epi = EPI_BIAS_RESID_LN: xt += a w^T + bias in the row-tiled stream; returns (xb, stats_out))."""
+    require_cuda(a, w, bias, colsum, stats, xt, out, out2)
+    M, K = a.shape
+    N = w.shape[0]
+    mp = m_pad_of(M)
+    fold = _lib.LnFold()
+    fold.m_pad = mp
+    fold.eps = eps
+    if colsum is not None:
+        fold.colsum = colsum.data_ptr()
+        fold.stats = stats.data_ptr()
+    if epi == _lib.EPI_BIAS_RESID_LN:
+        stats_out = torch.zeros(mp, _lib.LN_SLOTS, 2, dtype=torch.float32, device=a.device) if stats_out is None else stats_out
+        fold.xt = xt.data_ptr()
+        fold.stats_out = stats_out.data_ptr()
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device) if out is None else out
+    elif out is None:
+        if epi in (_lib.EPI_BIAS_BF16, _lib.EPI_BIAS_GELU_BF16):
+            out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+        elif epi == _lib.EPI_QKV_SPLIT:
+            d = N // 3
+            out = torch.empty(M, 2 * d, dtype=torch.bfloat16, device=a.device)
+            out2 = torch.zeros((M // tokens) * d, tok_pad, dtype=torch.bfloat16, device=a.device)
+        elif epi == _lib.EPI_KFEAT_F16:
+            out = torch.empty((M // tokens) * (tokens - 1), N, dtype=torch.float16, device=a.device)
+        else:
+            raise _lib.VittfError("vittf_gemm_bf16_ln: unsupported epilogue")
+    import ctypes as C
+    check(load().vittf_gemm_bf16_ln(ptr(a), ptr(w), ptr(bias), ptr(out), ptr(out2), M, N, K, epi, tokens, tok_pad, C.byref(fold),
+                                    stream_ptr(a.device)), "vittf_gemm_bf16_ln")
+    if epi == _lib.EPI_BIAS_RESID_LN:
+        return out, stats_out
+    return (out, out2) if epi == _lib.EPI_QKV_SPLIT else out
+
+
 @_on_device
 def attention(qk, vt, batch, tokens, heads, tok_pad):
     require_cuda(qk, vt)

@@ -7,6 +7,7 @@ them once (bf16 copies, patch-embed folding, pos-embed interpolation) and drives
 """
 import ctypes as C
 import math
+import os
 import weakref
 
 import torch
@@ -31,6 +32,19 @@ def fold_patch_embed(weight, bias):
     b1 = bias.detach().double().cpu() - (w * mean / std).sum(dim=(1, 2, 3))
     d = w1.shape[0]
     return w1.reshape(d, -1).t().contiguous().float(), b1.float()
+
+
+def fold_layernorm(weight, bias, ln_w, ln_b):
+    """LayerNorm folded into the Linear that follows it (gemm.cu, vittf_gemm_bf16_ln):
+        LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + b'     with W' = W * gamma, b' = b + W beta.
+    Returns (W' as bf16, b' fp32, colsum fp32 = row sums of the ROUNDED W', so that the mean term cancels exactly what the
+    tensor cores accumulate)."""
+    w = weight.detach().double().cpu()
+    g, be = ln_w.detach().double().cpu(), ln_b.detach().double().cpu()
+    w_folded = (w * g[None, :]).float().to(torch.bfloat16)
+    b_folded = (bias.detach().double().cpu() + w @ be).float()
+    colsum = w_folded.double().sum(dim=1).float()
+    return w_folded, b_folded, colsum
 
 
 def interpolate_pos_embed(pos_embed, cls_token, patch, im0, im1):
@@ -70,6 +84,9 @@ class VitEngine:
         self.max_tokens = max_tokens
         dev = self.device
         self._keep = []      # device tensors referenced by raw pointers inside the engine
+        # norm1 / norm2 folded into qkv / fc1 (no LayerNorm pass; VITTF_NO_LNFOLD=1 keeps the separate LayerNorm kernel: A/B)
+        self.ln_fold = (os.environ.get("VITTF_NO_LNFOLD") is None and self.mlp_hidden >= 2 * self.embed_dim
+                        and 0 < load().vittf_gemm_ln_slots(self.embed_dim) <= _lib.LN_SLOTS)
 
         def f32(t):
             t = t.detach().to(dev, torch.float32).contiguous()
@@ -104,12 +121,17 @@ class VitEngine:
             if "ls2" in mods and hasattr(mods["ls2"], "gamma"):
                 g2 = mods["ls2"].gamma.detach().float().cpu()
                 fc2_w, fc2_b = fc2_w * g2[:, None], fc2_b * g2
+            fc1_w, fc1_b = blk.mlp.fc1.weight.detach().float().cpu(), blk.mlp.fc1.bias.detach().float().cpu()
             fields = dict(ln1_w=f32(blk.norm1.weight), ln1_b=f32(blk.norm1.bias),
-                          qkv_w=bf16(qkv_w), qkv_b=f32(qkv_b),
                           proj_w=bf16(proj_w), proj_b=f32(proj_b),
                           ln2_w=f32(blk.norm2.weight), ln2_b=f32(blk.norm2.bias),
-                          fc1_w=bf16(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias),
                           fc2_w=bf16(fc2_w), fc2_b=f32(fc2_b))
+            if self.ln_fold:
+                qw, qb, qs = fold_layernorm(qkv_w, qkv_b, blk.norm1.weight, blk.norm1.bias)
+                fw, fb, fs = fold_layernorm(fc1_w, fc1_b, blk.norm2.weight, blk.norm2.bias)
+                fields.update(qkv_w=bf16(qw), qkv_b=f32(qb), qkv_colsum=f32(qs), fc1_w=bf16(fw), fc1_b=f32(fb), fc1_colsum=f32(fs))
+            else:
+                fields.update(qkv_w=bf16(qkv_w), qkv_b=f32(qkv_b), fc1_w=bf16(fc1_w), fc1_b=f32(fc1_b))
             for k, v in fields.items():
                 setattr(arr[i], k, v.data_ptr())
         self._blocks = arr
