@@ -540,7 +540,11 @@ int launch_lowres_mma_one(const CUtensorMap& tm3, const CUtensorMap& tm1, int F,
     return VITTF_OK;
 }
 
-// first <= 32 prototypes + Gram planes fused; prototypes beyond 32 on the dots-only tensor-core kernel
+// first <= 64 prototypes + Gram planes fused (one read of the feature volume); prototypes beyond 64 on the dots-only
+// tensor-core kernel
+#ifndef GM_MAX_PROTOS
+#define GM_MAX_PROTOS 64
+#endif
 int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const float* protos, int A, float* dots, float* gram,
                       cudaStream_t s, int layout = 0, int xa = 0, int xb = -1) {
     if (xb < 0) xb = w;
@@ -554,13 +558,14 @@ int launch_lowres_mma(const __half* feats, int F, int w, int h, int d, const flo
     const uint32_t box3[4] = {GM_ZB, 3, 1, GM_KF}, box1[4] = {GM_ZB, 1, 1, GM_KF};
     VITTF_CHECK(vittf_make_tmap(&tm3, feats, 2, 4, dims, strides, box3, false));
     VITTF_CHECK(vittf_make_tmap(&tm1, feats, 2, 4, dims, strides, box1, false));
-    const int a0 = A < 32 ? A : 32;
+    const int a0 = A < GM_MAX_PROTOS ? A : GM_MAX_PROTOS;
     int rc;
-    if (a0 > 16) rc = launch_lowres_mma_one<4>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, xa, xb, s);
+    if (a0 > 32) rc = launch_lowres_mma_one<8>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, xa, xb, s);
+    else if (a0 > 16) rc = launch_lowres_mma_one<4>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, xa, xb, s);
     else if (a0 > 8) rc = launch_lowres_mma_one<2>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, xa, xb, s);
     else rc = launch_lowres_mma_one<1>(tm3, tm1, F, w, h, d, protos, a0, dots, gram, sa, sv, xa, xb, s);
     if (rc != VITTF_OK) return rc;
-    if (A > 32) VITTF_CHECK(launch_dots_mma(feats, F, n_lr, protos, A, dots, s, 32, sa, sv, static_cast<int64_t>(xa) * h * d, static_cast<int64_t>(xb) * h * d));
+    if (A > GM_MAX_PROTOS) VITTF_CHECK(launch_dots_mma(feats, F, n_lr, protos, A, dots, s, GM_MAX_PROTOS, sa, sv, static_cast<int64_t>(xa) * h * d, static_cast<int64_t>(xb) * h * d));
     VITTF_CHECK_CUDA(cudaGetLastError());
     return VITTF_OK;
 }

@@ -173,8 +173,11 @@ extern "C" int vittf_vit_k_features(vittf_vit* v, const void* vol, int vol_dtype
     const int D = c.embed_dim;
     const int M = B * tokens;
     const int tok_pad = tok_pad_of(tokens);
-    // padding columns of V^T are read (times P = 0) by the last key block: they must be finite
-    VITTF_CHECK_CUDA(cudaMemsetAsync(w.vt, 0, w.vt_bytes, s));
+    // padding columns [tokens, tok_pad) of V^T are read (times P = 0) by the last key block: they must be finite.  Only they
+    // are cleared (B * D rows of tok_pad - tokens elements); the QKV epilogue writes every other element.
+    if (tok_pad > tokens)
+        VITTF_CHECK_CUDA(cudaMemset2DAsync(w.vt + tokens, static_cast<size_t>(tok_pad) * 2, 0, static_cast<size_t>(tok_pad - tokens) * 2,
+                                           static_cast<size_t>(B) * D, s));
     const bool fold = v->blocks[0].qkv_colsum != nullptr;
     if (fold) {
         // LayerNorm folded into the GEMMs (gemm.cu): x = row-tiled fp32 stream, xn = its raw bf16 copy, stats = row sums.
