@@ -440,35 +440,54 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 // Entry into the LayerNorm-folded GEMM chain (gemm.cu): the row-major fp32 tokens of the patch embedding become the
-// row-tiled residual stream xt[m_pad/32][D/4][32][4], its raw bf16 copy and the per-row (sum, sum of squares).  One warp
-// per row; runs once per forward (the blocks' LayerNorms themselves never run as a pass).
+// row-tiled residual stream xt[m_pad/32][D/4][32][4], its raw bf16 copy and the per-row (sum, sum of squares).  One CTA
+// per group of 32 rows, 128 columns at a time: rows are read and the bf16 copy written with a warp per row (512 / 256
+// contiguous bytes per instruction), the fp32 values cross a padded shared-memory tile and leave as the 16 KB contiguous
+// block that 32 rows x 128 columns occupy in the tiled layout.  Runs once per forward (the blocks' LayerNorms themselves
+// never run as a pass).
 // ---------------------------------------------------------------------------------------------
 template <int V4>
 __global__ void __launch_bounds__(256) ln_prepare_kernel(const float* __restrict__ x, float* __restrict__ xt,
                                                          __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats,
                                                          int64_t rows) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
     constexpr int D = 128 * V4;
-    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
-    float4* xtr = reinterpret_cast<float4*>(xt) + (row >> 5) * (D / 4) * 32 + (row & 31);
-    uint2* yr = reinterpret_cast<uint2*>(xb + row * D);
-    float sum = 0.0f, sq = 0.0f;
+    __shared__ float4 tile[32][33];                       // [row][column group], pitch 33: the transposed reads are conflict-free
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * 32;
+    float4* xt_grp = reinterpret_cast<float4*>(xt) + row0 * (D / 4);       // this group's block of the tiled stream
+    float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int ch = 0; ch < V4; ++ch) {
 #pragma unroll
-    for (int i = 0; i < V4; ++i) {
-        const float4 v = xr[lane + 32 * i];
-        sum += (v.x + v.y) + (v.z + v.w);
-        sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-        xtr[static_cast<int64_t>(lane + 32 * i) * 32] = v;
-        yr[lane + 32 * i] = make_uint2(ptx::pack_bf16x2(v.x, v.y), ptx::pack_bf16x2(v.z, v.w));
+        for (int k = 0; k < 4; ++k) {
+            const int r = warp * 4 + k;
+            const int64_t row = row0 + r;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (row < rows) {
+                v = reinterpret_cast<const float4*>(x + row * D)[ch * 32 + lane];
+                reinterpret_cast<uint2*>(xb + row * D)[ch * 32 + lane] = make_uint2(ptx::pack_bf16x2(v.x, v.y), ptx::pack_bf16x2(v.z, v.w));
+            }
+            sum[k] += (v.x + v.y) + (v.z + v.w);
+            sq[k] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            tile[r][lane] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = threadIdx.x + 256 * k;          // element (column group j, row r) of the chunk, r fastest
+            xt_grp[(ch * 32) * 32 + e] = tile[e & 31][e >> 5];
+        }
+        __syncthreads();
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], o);
+            sq[k] += __shfl_xor_sync(0xffffffffu, sq[k], o);
+        }
+        const int64_t row = row0 + warp * 4 + k;
+        if (lane < VITTF_LN_SLOTS) stats[row * VITTF_LN_SLOTS + lane] = lane == 0 ? make_float2(sum[k], sq[k]) : make_float2(0.0f, 0.0f);
     }
-    if (lane < VITTF_LN_SLOTS) stats[row * VITTF_LN_SLOTS + lane] = lane == 0 ? make_float2(sum, sq) : make_float2(0.0f, 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -845,7 +864,7 @@ extern "C" int vittf_ln_prepare(const float* x, float* xt, void* xb_bf16, float*
     VITTF_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, "vittf_ln_prepare: D=%d must be a multiple of 128 in [128,1024]", D);
     VITTF_REQUIRE(m_pad >= rows && m_pad % 256 == 0, "vittf_ln_prepare: m_pad must be rows rounded up to a multiple of 256");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, 8));
+    const unsigned grid = static_cast<unsigned>(ceil_div_ll(rows, 32));          // whole 32-row groups: padding rows are written as zeros
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(xb_bf16);
     float2* st = reinterpret_cast<float2*>(stats);
     switch (D / 128) {
