@@ -85,7 +85,10 @@ class VitEngine:
         dev = self.device
         self._keep = []      # device tensors referenced by raw pointers inside the engine
         # norm1 / norm2 folded into qkv / fc1 (no LayerNorm pass; VITTF_NO_LNFOLD=1 keeps the separate LayerNorm kernel: A/B)
-        self.ln_fold = (os.environ.get("VITTF_NO_LNFOLD") is None and self.mlp_hidden >= 2 * self.embed_dim
+        # -- for embed dims the 256-wide CTA-pair tiles cover (ViT-B, ViT-L); at D = 384 the residual-stream epilogue would run on
+        # 128-wide single-CTA tiles and loses what the fold saves (ViT-S/8 step: 457.8 ms folded, 456.2 ms with the kernel)
+        self.ln_fold = (os.environ.get("VITTF_NO_LNFOLD") is None and self.embed_dim % 256 == 0
+                        and self.mlp_hidden >= 2 * self.embed_dim
                         and 0 < load().vittf_gemm_ln_slots(self.embed_dim) <= _lib.LN_SLOTS)
 
         def f32(t):
