@@ -273,12 +273,19 @@ def test_other_backbones_match_oracle(arch, depth):
     assert _cos_min(out, ref) >= 0.995
 
 
-@pytest.mark.parametrize("switch", ["VITTF_NO_LNFOLD", "VITTF_GEMM_NO_PAIRS"])
-def test_engine_switches(switch):
-    """The engine's two A/B switches select code the default path does not run: VITTF_NO_LNFOLD = separate LayerNorm kernel +
-    reduce-add residual epilogue (the default folds norm1 / norm2 into the GEMMs around them), VITTF_GEMM_NO_PAIRS =
-    single-CTA GEMM tiles (the default runs N % 256 == 0 as CTA pairs, tcgen05 cta_group::2).  The golden feature volumes, the
-    full-depth ViT-S/8 and ViT-B/8 checks and the GEMM unit tests must hold under both."""
+@pytest.mark.parametrize("switch,select", [
+    ("VITTF_NO_LNFOLD", "reference_golden or full_depth or other_backbones or (test_gemm and not test_gemm_ln)"),
+    ("VITTF_GEMM_NO_PAIRS", "reference_golden or full_depth or other_backbones or (test_gemm and not test_gemm_ln)"),
+    ("VITTF_ATTN_SAFE_ONLY", "reference_golden or full_depth"),
+    ("VITTF_PE_NO_MMA", "reference_golden or patch_embed or full_depth_512"),
+], ids=["VITTF_NO_LNFOLD", "VITTF_GEMM_NO_PAIRS", "VITTF_ATTN_SAFE_ONLY", "VITTF_PE_NO_MMA"])
+def test_engine_switches(switch, select):
+    """The engine's A/B switches select code the default path does not run: VITTF_NO_LNFOLD = separate LayerNorm kernel +
+    reduce-add residual epilogue for ViT-B / ViT-L too (the default folds norm1 / norm2 into the GEMMs around them),
+    VITTF_GEMM_NO_PAIRS = single-CTA GEMM tiles (the default runs N % 256 == 0 as CTA pairs, tcgen05 cta_group::2),
+    VITTF_ATTN_SAFE_ONLY = the online-softmax attention kernel alone (default: max-free first pass + safe pass over flagged
+    items), VITTF_PE_NO_MMA = the FMA-pipe patch embedding for patch 8.  The golden feature volumes, the full-depth
+    ViT-S/8 and ViT-B/8 checks and the unit tests of the switched kernels must hold under each."""
     import os
     import subprocess
     import sys
@@ -287,7 +294,6 @@ def test_engine_switches(switch):
     env = dict(os.environ)
     env[switch] = "1"
     r = subprocess.run([sys.executable, "-m", "pytest", str(here / "test_gpu_vit.py"), str(here / "test_gpu_gemm.py"), "-x", "-q", "-m", "gpu",
-                        "-p", "no:cacheprovider", "-k",
-                        "reference_golden or full_depth or other_backbones or (test_gemm and not test_gemm_ln)"],
-                       env=env, capture_output=True, text=True, cwd=str(here.parent))
+                        "-p", "no:cacheprovider", "-k", f"({select}) and not engine_switches"],
+                       env=env, capture_output=True, text=True, cwd=str(here.parent), timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
