@@ -77,3 +77,31 @@ def test_sharded_feature_volume_equals_oracle_gloo(tmp_path):
     ref = ofv.feature_volume(vol, dino_vit.build("vits8", seed=0, depth=2), patch=8, fos=8, batch_size=4)
     got = torch.load(out)
     assert got.dtype == torch.float16 and torch.equal(got, ref)
+
+
+def test_x_slab_planning_covers_the_footprint():
+    """dist.x_range / similarity.lowres_x_planes (a rank needs the low-res planes under its output slab +- 1):
+    the slabs tile the output exactly once, and every low-res plane a slab's trilinear footprint reads (index rule of
+    F.interpolate(align_corners=False), predict_ntf.py:87) lies inside the planes pass 1 evaluates for it."""
+    from vittf_b200 import dist as vdist
+    from vittf_b200.similarity import lowres_x_planes
+    for lr_w, u in ((64, 2), (64, 4), (64, 8), (128, 4), (6, 2), (5, 8)):
+        out_w = lr_w * u
+        for world in (1, 2, 3, 8):
+            covered = []
+            for rank in range(world):
+                x0, x1 = vdist.x_range(out_w, world, rank)
+                covered += list(range(x0, x1))
+                if x1 <= x0:
+                    continue
+                xa, xb = lowres_x_planes(lr_w, out_w, (x0, x1))
+                assert 0 <= xa < xb <= lr_w
+                for x in range(x0, x1):
+                    src = max((x + 0.5) / u - 0.5, 0.0)
+                    i0 = int(src)
+                    i1 = min(i0 + 1, lr_w - 1)
+                    assert xa <= i0 < xb, (lr_w, u, world, rank, x)
+                    if src - i0 > 0.0:                       # (weight 0 at the clamped border: the plane is not read)
+                        assert xa <= i1 < xb, (lr_w, u, world, rank, x)
+            assert covered == list(range(out_w))
+    assert lowres_x_planes(64, 200, (0, 10)) is None          # non-integer factor: every plane

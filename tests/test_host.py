@@ -105,3 +105,32 @@ def test_luma_lut_matches_oracle():
     from vittf_b200.bilateral_solver3d import luma_lut
     for s in (3, 4, 5, 7, 2.5):
         assert np.array_equal(luma_lut(s), bls.luma_lut(s))
+
+
+def test_layernorm_fold_identity():
+    """vit.fold_layernorm: LN(x) W^T + b == rstd * (x W'^T - mean * colsum(W')) + b' with W' = W * gamma (bf16), b' = b + W beta,
+    for the statistics the GEMM epilogues form from partial (sum, sum of squares) -- evaluated in fp64 on the folded
+    (rounded) weights, so that only the fold algebra is under test (gemm.cu header, /root/reference hub Block.forward)."""
+    from vittf_b200.vit import fold_layernorm
+    g = torch.Generator().manual_seed(3)
+    D, N, M = 96, 40, 17
+    w, b = torch.randn(N, D, generator=g) * 0.1, torch.randn(N, generator=g) * 0.1
+    gamma, beta = 1.0 + 0.3 * torch.randn(D, generator=g), 0.2 * torch.randn(D, generator=g)
+    x = torch.randn(M, D, generator=g) * torch.logspace(-1, 1, M)[:, None] + 0.4
+    wf, bf, cs = fold_layernorm(w, b, gamma, beta)
+    assert wf.dtype == torch.bfloat16 and bf.dtype == torch.float32 and cs.dtype == torch.float32
+    assert torch.allclose(cs.double(), wf.double().sum(1), rtol=0, atol=1e-6)
+    xd = x.double()
+    # partial sums over 3 column slices, as the residual-stream epilogue writes them
+    s = sum(xd[:, i:i + 32].sum(1) for i in range(0, D, 32))
+    sq = sum((xd[:, i:i + 32] ** 2).sum(1) for i in range(0, D, 32))
+    mean = s / D
+    rstd = (sq / D - mean ** 2 + 1e-6).rsqrt()
+    got = rstd[:, None] * (xd @ wf.double().t() - mean[:, None] * cs.double()[None, :]) + bf.double()
+    # the same weights without the fold: gamma is inside wf, so un-fold it for the reference
+    ln_unit = F.layer_norm(xd, (D,), None, None, eps=1e-6)                    # (x - mean) * rstd
+    ref = ln_unit @ wf.double().t() + bf.double()
+    assert torch.allclose(got, ref, rtol=1e-9, atol=1e-9)
+    # and against the textbook form within the bf16 rounding of W * gamma
+    full = F.layer_norm(xd, (D,), gamma.double(), beta.double(), eps=1e-6) @ w.double().t() + b.double()
+    assert (got - full).abs().max().item() < 2e-2 * max(1.0, full.abs().max().item())
