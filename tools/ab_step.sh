@@ -6,7 +6,8 @@ REPS=${REPS:-2}
 for r in $(seq 1 $REPS); do
   for spec in "$@"; do
     name="${spec%%:*}"; envs="${spec#*:}"; [ "$envs" = "$spec" ] && envs=""
-    env $envs python bench.py --workload ${WORKLOAD:-cfg3} --steps ${STEPS:-3} --warmup ${WARMUP:-2} --no-cpu-baseline ${BATCH:+--batch $BATCH} > gpurun_out/ab_${name}_$r.json 2> gpurun_out/ab_${name}_$r.err
+    batch=""; for kv in $envs; do case "$kv" in BATCH=*) batch="--batch ${kv#BATCH=}";; esac; done
+    env $envs python bench.py --workload ${WORKLOAD:-cfg3} --steps ${STEPS:-3} --warmup ${WARMUP:-2} --no-cpu-baseline $batch > gpurun_out/ab_${name}_$r.json 2> gpurun_out/ab_${name}_$r.err
     python - "$name" "$r" <<'P'
 import json, sys
 n, r = sys.argv[1:3]

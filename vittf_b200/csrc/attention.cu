@@ -32,7 +32,10 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int KV_STAGES = 3;
+#ifndef KV_STAGES_V
+#define KV_STAGES_V 3
+#endif
+constexpr int KV_STAGES = KV_STAGES_V;
 constexpr int ATT_THREADS = 384;
 constexpr int Q_TILE_BYTES = BQ * HD * 2;        // 16 KB
 constexpr int K_TILE_BYTES = BKV * HD * 2;       // 16 KB
