@@ -722,9 +722,16 @@ __device__ __forceinline__ uint32_t bit_range(int lo, int hi) {
 }
 
 constexpr int UP_PD = 4;            // prefetch distance of the corner dots, in prototypes
+// CTAs per SM of the factor-4 instantiation: 3 (168 registers, 64-164 B of spills in the prototype loop) measured 324 us
+// against 227 us for 2 (203 registers, no spills) at 384 x 64^3 -> 256^3, 32 prototypes -- the kernel is short of issue
+// slots, not of warps
+#ifndef UP_BLOCKS_U4
+#define UP_BLOCKS_U4 2
+#endif
+#define UP_MIN_BLOCKS(U) ((U) == 4 ? UP_BLOCKS_U4 : 2)
 
 template <int U, int EXPK>
-__global__ void __launch_bounds__(128, 2) sim_upsample_mma_kernel(UpParams q, int cz_lo, int ncz, int tiles_per_x, int total_tasks, int cx_lo) {
+__global__ void __launch_bounds__(128, UP_MIN_BLOCKS(U)) sim_upsample_mma_kernel(UpParams q, int cz_lo, int ncz, int tiles_per_x, int total_tasks, int cx_lo) {
     constexpr int NSUB = U == 8 ? 8 : 1;             // sub-blocks of 64 outputs per cell
     extern __shared__ __align__(16) uint8_t um_smem[];
     int* s_off = reinterpret_cast<int*>(um_smem);
