@@ -278,13 +278,15 @@ def test_other_backbones_match_oracle(arch, depth):
     ("VITTF_GEMM_NO_PAIRS", "reference_golden or full_depth or other_backbones or (test_gemm and not test_gemm_ln)"),
     ("VITTF_ATTN_SAFE_ONLY", "reference_golden or full_depth"),
     ("VITTF_PE_NO_MMA", "reference_golden or patch_embed or full_depth_512"),
-], ids=["VITTF_NO_LNFOLD", "VITTF_GEMM_NO_PAIRS", "VITTF_ATTN_SAFE_ONLY", "VITTF_PE_NO_MMA"])
+    ("VITTF_GEMM_EPI16", "test_gemm and not test_gemm_ln"),
+], ids=["VITTF_NO_LNFOLD", "VITTF_GEMM_NO_PAIRS", "VITTF_ATTN_SAFE_ONLY", "VITTF_PE_NO_MMA", "VITTF_GEMM_EPI16"])
 def test_engine_switches(switch, select):
     """The engine's A/B switches select code the default path does not run: VITTF_NO_LNFOLD = separate LayerNorm kernel +
     reduce-add residual epilogue for ViT-B / ViT-L too (the default folds norm1 / norm2 into the GEMMs around them),
     VITTF_GEMM_NO_PAIRS = single-CTA GEMM tiles (the default runs N % 256 == 0 as CTA pairs, tcgen05 cta_group::2),
     VITTF_ATTN_SAFE_ONLY = the online-softmax attention kernel alone (default: max-free first pass + safe pass over flagged
-    items), VITTF_PE_NO_MMA = the FMA-pipe patch embedding for patch 8.  The golden feature volumes, the full-depth
+    items), VITTF_PE_NO_MMA = the FMA-pipe patch embedding for patch 8, VITTF_GEMM_EPI16 = 16 instead of 8 epilogue warps for the bf16
+    epilogues of the CTA-pair GEMM tiles.  The golden feature volumes, the full-depth
     ViT-S/8 and ViT-B/8 checks and the unit tests of the switched kernels must hold under each."""
     import os
     import subprocess

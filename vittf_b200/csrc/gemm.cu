@@ -37,9 +37,14 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 384;
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
+// EW epilogue warps: 8 (two per TMEM lane quarter, half of the tile's columns each) or 16 (four per quarter, a quarter of
+// the columns each).  With K = 768 (qkv, fc1 of ViT-B) a 128 x 256 tile's main loop is ~6000 tensor cycles and 8 warps need
+// about as long for its epilogue (dependent chains: TMEM load -> bias / LayerNorm scalars -> GELU -> pack -> staging -> TMA):
+// with the epilogue skipped the same launches ran 23 % faster (profiles/r2_gemm_epilogue_bound.log).  16 warps (64 columns
+// = ONE 64-column staging tile per thread and tile) are selectable for the bf16 epilogues of the 256-wide pair tiles
+// (VITTF_GEMM_EPI16) but lose in the power-capped step; what did pay was shortening the 8-warp epilogue's live ranges
+// (one 32-column chunk at a time: no spills, 2063 -> 2028 ms at equal clocks).
+constexpr int gemm_threads(int ew) { return 128 + ew * 32; }
 constexpr int STAGING_BYTES = 32 * 128;  // one 32-row x 128-byte tile per epilogue warp
 
 // CG = 2: CTA pair (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256 x BN tile: each CTA stages ITS 128 rows of
@@ -47,16 +52,16 @@ constexpr int STAGING_BYTES = 32 * 128;  // one 32-row x 128-byte tile per epilo
 // accumulator rows.  Per CTA and K block that is 32 KB from L2 instead of 48 KB for the same 128 x 256 x 64 MACs -- the
 // single-CTA kernel at 1.28 PFLOP/s pulls ~52 B/clk/SM, which is what the L2 slices deliver chip-wide (the GEMMs were
 // L2-bandwidth-bound, not tensor-bound).
-template <int BN, int CG = 1>
+template <int BN, int CG = 1, int EW = 8>
 struct GemmCfg {
     static constexpr int B_ROWS = BN / CG;                     // W rows staged per CTA
-    static constexpr int STAGES = B_ROWS <= 128 ? 6 : 4;
+    static constexpr int STAGES = B_ROWS <= 128 ? (EW == 16 ? 5 : 6) : 4;    // (16 staging tiles take one stage's room)
     static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;   // TMEM column offset of the second accumulator
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 1024 + 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EW * STAGING_BYTES + 1024 + 512;
 };
 
 struct GemmParams {
@@ -129,16 +134,20 @@ __device__ __forceinline__ void gelu_tanh2(float& x0, float& x1) {
 // byte offset of 16-byte chunk `chunk` of row `row` inside a 128B-swizzled 32 x 128 B staging tile
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-template <int BN, int EPI, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int EPI, int CG, int EW>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                      const __grid_constant__ CUtensorMap tm_out, GemmParams p) {
-    using Cfg = GemmCfg<BN, CG>;
+    using Cfg = GemmCfg<BN, CG, EW>;
     static_assert(CG == 1 || CG == 2, "single CTA or CTA pair");
+    static_assert(EW == 8 || EW == 16, "two or four epilogue warps per TMEM lane quarter");
+    static_assert(EW == 8 || (EPI != VITTF_EPI_BIAS_RESID_F32 && EPI != VITTF_EPI_BIAS_RESID_LN && EPI != VITTF_EPI_KFEAT_F16),
+                  "the residual-stream epilogues (128-column partial sums) and the K-feature epilogue run on 8 warps");
+    constexpr int COLS = BN / (EW / 4);                        // columns of the tile one epilogue warp owns
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * STAGING_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EW * STAGING_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + Cfg::STAGES;
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
@@ -162,7 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full[i], 1);
-            ptx::mbar_init(&tmem_empty[i], CG * EPI_THREADS);     // the leader's barrier collects both CTAs' epilogue threads
+            ptx::mbar_init(&tmem_empty[i], CG * EW * 32);     // the leader's barrier collects both CTAs' epilogue threads
         }
         ptx::fence_barrier_init();
     }
@@ -179,7 +188,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     // Roles are dispatched per WARP (uniform) and the issuing lane is chosen with elect.sync: a branch on
     // threadIdx.x would make ptxas wrap every TMA / MMA instruction in a divergence ("waterfall") loop.
     // Only that one lane polls the mbarriers.
-    if (warp == 0 && ptx::elect_one()) {
+    // EW = 16: the CTA's register pool is what it was launched with, 640 threads x 96; the producer / issuer / allocator
+    // warpgroup gives 40 per thread back (128 x 40 = 5120) and the four epilogue warpgroups take 8 more each (512 x 8 = 4096
+    // <= 5120: a claim larger than what was released would block forever).  The setmaxnreg instructions sit INSIDE the role
+    // branches: ptxas only allocates against the raised limit in code they dominate.
+    if (warp < 4) {
+      if constexpr (EW == 16) ptx::setmaxnreg_dec<56>();
+      if (warp == 0 && ptx::elect_one()) {
         // ---------------- TMA producer ----------------
         ptx::prefetch_tmap(&tm_a);
         ptx::prefetch_tmap(&tm_b);
@@ -203,7 +218,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && rank == 0 && ptx::elect_one()) {
+      } else if (warp == 1 && rank == 0 && ptx::elect_one()) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM * CG, BN);
         int stage = 0;
@@ -236,12 +251,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+      }
+    } else {
+        if constexpr (EW == 16) ptx::setmaxnreg_inc<104>();
         // ---------------- epilogue ----------------
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;       // which half of the tile's columns
+        const int half = (warp - 4) >> 2;       // which half (EW = 8) / quarter (EW = 16) of the tile's columns
         uint8_t* stg = staging + (warp - 4) * STAGING_BYTES;
-        constexpr int CHUNKS = BN / 2 / 32;
+        constexpr int CHUNKS = COLS / 32;
         if (ptx::elect_one()) ptx::prefetch_tmap(&tm_out);
         int it = 0;
         // accumulator drained: tell the (leader's) MMA issuer
@@ -256,7 +273,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const int as = it & 1;
             const int row0 = m_blk * BM + q * 32;
             const int row = row0 + lane;
-            const int n0 = n_blk * BN + half * (BN / 2);
+            const int n0 = n_blk * BN + half * COLS;
             // LayerNorm fold, consumer side: the two row scalars (plain epilogue: rstd = 1, -mean * rstd = 0)
             float rstd = 1.0f, nmr = 0.0f;
             const float* cs = p.bias;
@@ -279,7 +296,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             if constexpr (EPI == VITTF_EPI_BIAS_RESID_LN) {
                 // a warp's slice of the tile (32 rows x BN/2 columns) is ONE contiguous block of the row-tiled stream
                 auto slice = [&](int mb, int nb) {
-                    return reinterpret_cast<float4*>(p.xt) + (static_cast<size_t>(mb * 4 + q) * (p.N / 4) + (nb * BN + half * (BN / 2)) / 4) * 32;
+                    return reinterpret_cast<float4*>(p.xt) + (static_cast<size_t>(mb * 4 + q) * (p.N / 4) + (nb * BN + half * COLS) / 4) * 32;
                 };
                 xrow = slice(m_blk, n_blk) + lane;
 #pragma unroll
@@ -287,7 +304,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
             ptx::mbar_wait(&tmem_full[as], (it >> 1) & 1);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE + half * (BN / 2);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE + half * COLS;
             // stage_out(): the 32 x 128 B tile in `stg` is complete -> hand it to the TMA engine
             auto stage_out = [&](int col, bool reduce) {
                 ptx::fence_proxy_async();
@@ -381,44 +398,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 const int two_d = (p.N / 3) * 2;
 #pragma unroll
                 for (int c = 0; c < CHUNKS; c += 2) {
-                    float v0[32], v1[32];
-                    load_biased(c, v0);
-                    load_biased(c + 1, v1);
-                    if (c == CHUNKS - 2) {
-                        release_acc(as);
-                    }
                     const int n = n0 + c * 32;
-                    if (EPI == VITTF_EPI_QKV_SPLIT && n >= two_d) {
-                        // V third: stored transposed per (image, head): vt[(img*heads+h)*64 + d][token]; lanes hold
-                        // consecutive tokens, so each store instruction writes 64 contiguous bytes
-                        if (row < p.M) {
-                            const int img = row / p.tokens;
-                            const int tok = row - img * p.tokens;
-                            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out2) +
-                                                 (static_cast<size_t>(img) * p.heads * 64 + (n - two_d)) * p.tok_pad + tok;
+                    // V third of the QKV projection: stored transposed per (image, head): vt[(img*heads+h)*64 + d][token];
+                    // lanes hold consecutive tokens, so each store instruction writes 64 contiguous bytes
+                    const bool vt_third = EPI == VITTF_EPI_QKV_SPLIT && n >= two_d;          // (warp-uniform)
+                    // one 32-column chunk at a time (32 values + the TMEM load live): the two chunks share a staging tile
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(i) * p.tok_pad] = __float2bfloat16_rn(v0[i]);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float v[32];
+                        load_biased(c + hh, v);
+                        if (c == CHUNKS - 2 && hh == 1) release_acc(as);
+                        if (vt_third) {
+                            if (row < p.M) {
+                                const int img = row / p.tokens;
+                                const int tok = row - img * p.tokens;
+                                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out2) +
+                                                     (static_cast<size_t>(img) * p.heads * 64 + (n - two_d) + 32 * hh) * p.tok_pad + tok;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(32 + i) * p.tok_pad] = __float2bfloat16_rn(v1[i]);
+                                for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(i) * p.tok_pad] = __float2bfloat16_rn(v[i]);
+                            }
+                            continue;
                         }
-                        continue;
-                    }
-                    if constexpr (EPI == VITTF_EPI_BIAS_GELU_BF16) {
+                        if constexpr (EPI == VITTF_EPI_BIAS_GELU_BF16) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
+                            for (int i = 0; i < 32; i += 2) {
 #ifdef VITTF_GELU_ERF
-                            gelu_erf2(v0[i], v0[i + 1]);
-                            gelu_erf2(v1[i], v1[i + 1]);
+                                gelu_erf2(v[i], v[i + 1]);
 #else
-                            gelu_tanh2(v0[i], v0[i + 1]);
-                            gelu_tanh2(v1[i], v1[i + 1]);
+                                gelu_tanh2(v[i], v[i + 1]);
 #endif
+                            }
                         }
+                        if (hh == 0) staging_free();
+                        put_bf16(4 * hh, v);
                     }
-                    staging_free();
-                    put_bf16(0, v0);
-                    put_bf16(4, v1);
-                    stage_out(n, false);
+                    if (!vt_third) stage_out(n, false);
                 }
             } else {  // VITTF_EPI_KFEAT_F16: CLS rows dropped (infer.py:202 `[:, 1:]`), fp16, direct stores
                 const int img = row / p.tokens;
@@ -459,9 +473,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
 }
 
-template <int BN, int EPI, int CG = 1>
+template <int BN, int EPI, int CG = 1, int EW = 8>
 int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, CG>;
+    using Cfg = GemmCfg<BN, CG, EW>;
     CUtensorMap tm_a, tm_b, tm_out;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
@@ -489,7 +503,7 @@ int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t 
         uint32_t box[2] = {64, 32};
         VITTF_CHECK(vittf_make_tmap(&tm_out, p.out, 2, 2, dims, strides, box, true));
     }
-    auto kern = gemm_bf16_kernel<BN, EPI, CG>;
+    auto kern = gemm_bf16_kernel<BN, EPI, CG, EW>;
     static PerDeviceMemo configured;
     if (!configured.cur()) {
         VITTF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -499,11 +513,11 @@ int launch_gemm(const void* A, const void* W, const GemmParams& p, cudaStream_t 
     const int units = vittf_num_sms() / CG;
     const int grid = (tiles < units ? tiles : units) * CG;
     if (CG == 1) {
-        kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, tm_out, p);
+        kern<<<grid, gemm_threads(EW), Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, tm_out, p);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.blockDim = dim3(gemm_threads(EW));
         cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -526,11 +540,17 @@ namespace {
 int gemm_dispatch(const void* A, const void* W, GemmParams p, int epi, cudaStream_t s) {
     const int N = p.N;
     static const bool pairs = getenv("VITTF_GEMM_NO_PAIRS") == nullptr;       // A/B switch: single-CTA tiles only
+    // A/B switch: 16 epilogue warps for the bf16 epilogues of the pair tiles.  Measured in the step (profiles/
+    // r2_ab_step_epilogue_warps.log): 2045 / 2051 ms against 2027 / 2029 ms for 8 warps -- stand-alone the K = 768 GEMMs are
+    // epilogue-bound (23 % faster with the epilogue skipped), under the power cap the extra warps cost more than they hide
+    static const bool wide_epi = getenv("VITTF_GEMM_EPI16") != nullptr;
     // (256 x 128 pair tiles for N % 256 != 0 were measured and dropped: ViT-S/8 step 462.8 ms with them, 457.8 ms without)
     // widest tile that divides N (a wider tile halves the shared-memory operand traffic per MMA); the bf16
     // epilogues stage 64-column tiles per warp, so they use 256 or 128; the fp32 reduce-add also takes 192
 #define VITTF_GEMM_BF16OUT(E)                                                       \
     do {                                                                            \
+        if (N % 256 == 0 && pairs && wide_epi && E != VITTF_EPI_BIAS_RESID_LN)      \
+            return launch_gemm<256, E == VITTF_EPI_BIAS_RESID_LN ? VITTF_EPI_BIAS_BF16 : E, 2, 16>(A, W, p, s); \
         if (N % 256 == 0 && pairs) return launch_gemm<256, E, 2>(A, W, p, s);      \
         if (N % 256 == 0) return launch_gemm<256, E>(A, W, p, s);                   \
         return launch_gemm<128, E>(A, W, p, s);                                     \
