@@ -1,9 +1,10 @@
 // Linear layers of the ViT (attn.qkv / attn.proj / mlp.fc1 / mlp.fc2 of the hub DINO model
 // that /root/reference/infer.py:177 runs): C = A W^T + bias with fused epilogues.
 //
-// B200 design: persistent, warp-specialised kernel, one CTA per SM.
+// B200 design: persistent, warp-specialised kernel, one CTA per SM -- or one CTA PAIR per TPC (CG = 2, below).
 //   warp 0    : TMA producer  (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 bf16 tiles, STAGES-deep ring)
-//   warp 1    : MMA issuer    (one thread, tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16, fp32 accum in TMEM)
+//   warp 1    : MMA issuer    (one thread, tcgen05.mma kind::f16, fp32 accum in TMEM: cta_group::1 128 x BN x 16, or, in
+//                              the leader CTA of a pair, cta_group::2 256 x BN x 16)
 //   warp 2    : TMEM allocator
 //   warps 4-11: epilogue      (tcgen05.ld 32x32b, one accumulator row per thread; two warps per TMEM lane
 //                              quarter, each owning half of the tile's columns).  Results are staged in a
@@ -49,9 +50,9 @@ constexpr int STAGING_BYTES = 32 * 128;  // one 32-row x 128-byte tile per epilo
 
 // CG = 2: CTA pair (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256 x BN tile: each CTA stages ITS 128 rows of
 // A and ITS half of the W rows (BN / 2), the leader's MMA reads both halves, each CTA's tensor memory receives its 128
-// accumulator rows.  Per CTA and K block that is 32 KB from L2 instead of 48 KB for the same 128 x 256 x 64 MACs -- the
-// single-CTA kernel at 1.28 PFLOP/s pulls ~52 B/clk/SM, which is what the L2 slices deliver chip-wide (the GEMMs were
-// L2-bandwidth-bound, not tensor-bound).
+// accumulator rows.  Per CTA and K block that is 32 KB from L2 instead of 48 KB for the same 128 x 256 x 64 MACs (the
+// single-CTA kernel at 1.28 PFLOP/s pulls ~52 B/clk/SM from the L2 slices).  Un-throttled (under ncu) the pairs run as
+// fast as the single-CTA tiles; in the power-capped step they are 7 % faster (GEMM time 836 -> 775 ms per volume).
 template <int BN, int CG = 1, int EW = 8>
 struct GemmCfg {
     static constexpr int B_ROWS = BN / CG;                     // W rows staged per CTA
